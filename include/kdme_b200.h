@@ -1,0 +1,179 @@
+/*
+ * kdme_b200.h -- C ABI of the B200-native joint-bilateral depth-enhancement path.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only;
+ * no torch / OpenCV types.  Every entry point cites the reference interface it
+ * replaces (paths relative to stevesuyao/KinectDepthMapEnhancement).
+ *
+ * Conventions
+ *   - All image pointers are DEVICE pointers unless the name says *_host.
+ *   - depth: float32, row-major y*width+x, millimetres, values <= 50 are holes
+ *     (JointBilateralFilter.cu:21).
+ *   - bgr: uint8 packed B,G,R with row pitch `step` bytes (cv::gpu::GpuMat::data /
+ *     ::step of a CV_8UC3 image; the reference assumes step == 3*width,
+ *     main.cpp:62 createContinuous).  step == 0 means 3*width.
+ *   - Every function returns 0 on success, KDME_EINVAL for a bad argument,
+ *     KDME_ENOTSUP for an unsupported configuration, or -(cudaError_t) for a CUDA
+ *     failure; kdme_last_error() returns a thread-local description.  (The
+ *     reference checks no return code at all, JointBilateralFilter.cpp:16-18.)
+ *   - Work is enqueued on the stream given at create time (0 = legacy default
+ *     stream, which preserves the reference's ordering with callers' default-stream
+ *     work, main.cpp:179-183).  Calls are asynchronous with respect to the host
+ *     unless stated.
+ *   - One handle per (device, stream); a handle is not thread-safe.
+ */
+#ifndef KDME_B200_H
+#define KDME_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDME_OK 0
+#define KDME_EINVAL (-100001)
+#define KDME_ENOTSUP (-100002)
+#define KDME_MAX_RADIUS 15
+
+const char *kdme_last_error(void);
+/* Library / build identification: "kdme_b200 <version> sm_100a". */
+const char *kdme_version(void);
+
+/* ======================= JointBilateralFilter ============================= */
+typedef struct jbf_handle jbf_handle;
+
+/* JointBilateralFilter::JointBilateralFilter(int width,int height)
+ *   JointBilateralFilter.h:11, JointBilateralFilter.cpp:8-20; the static consts
+ *   WindowSize/SpatialSigma/ColorSigma/DepthSigma (.cpp:3-6) become arguments
+ *   (reference values: radius 2, 70, 50, 20).  Builds the spatial LUT
+ *   (calcSpatialFilter, .cpp:31-40) and owns Filtered_Device / smooth_Device.
+ *   max_batch >= 1 sizes the internal smoothed-guide buffer for jbf_process_batch. */
+int jbf_create(jbf_handle **out, int width, int height, float sigma_spatial, float sigma_color,
+               float sigma_depth, int window_radius, int max_batch, int device, void *stream);
+
+/* JointBilateralFilter::~JointBilateralFilter -- JointBilateralFilter.cpp:21-30 */
+void jbf_destroy(jbf_handle *h);
+
+/* Guide pre-smooth parameters of cv::gpu::bilateralFilter(color, smooth, 5, 30.0f, 30.0f)
+ *   JointBilateralFilter.cu:285.  ksize == 0 disables the pre-smooth (guide used raw). */
+int jbf_set_presmooth(jbf_handle *h, int ksize, float sigma_color, float sigma_spatial);
+
+/* void JointBilateralFilter::Process(float* depth_device, cv::gpu::GpuMat color_image)
+ *   JointBilateralFilter.h:13, JointBilateralFilter.cu:283-290.  Result in
+ *   jbf_filtered_device(h). */
+int jbf_process(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step);
+
+/* Same operator over n_frames independent frames stored back to back (frame
+ * stride width*height elements / height*bgr_step bytes); out_dev receives
+ * n_frames planes.  One launch pair for the whole batch (the B200-native form of
+ * calling Process once per captured frame, main.cpp:86-101 loop shape). */
+int jbf_process_batch(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step,
+                      float *out_dev, int n_frames);
+
+/* Filter only (JointBilateralFilter.cu:289-290): guide4_dev is an ALREADY smoothed
+ * guide in the internal layout u8x4 {B,G,R,0}, row pitch guide_step bytes
+ * (multiple of 16).  Used by the row-band path and by stage-isolated parity tests. */
+int jbf_filter_guide4(jbf_handle *h, const float *depth_dev, const uint8_t *guide4_dev,
+                      size_t guide_step, float *out_dev, int n_frames);
+
+/* Pre-smooth only: packed BGR -> internal u8x4 guide (JointBilateralFilter.cu:285). */
+int jbf_presmooth(jbf_handle *h, const uint8_t *bgr_dev, size_t bgr_step, uint8_t *guide4_dev,
+                  size_t guide_step, int n_frames);
+
+/* Host-buffer convenience used for end-to-end timing: pinned or pageable HOST
+ * depth/bgr in, HOST filtered depth out; H2D, Process, D2H are pipelined in
+ * chunks of at most max_batch frames.  Synchronous (returns when out_host is
+ * complete).  Mirrors main.cpp:160-163 (upload) + :179 (Process) + :183 (download). */
+int jbf_process_host(jbf_handle *h, const float *depth_host, const uint8_t *bgr_host, size_t bgr_step,
+                     float *out_host, int n_frames);
+
+/* float* JointBilateralFilter::getFiltered_Device() const -- JointBilateralFilter.cpp:41-43.
+ * Borrowed pointer, valid until the next jbf_process / jbf_destroy. */
+float *jbf_filtered_device(jbf_handle *h);
+
+/* float* JointBilateralFilter::getFiltered_Host() const -- JointBilateralFilter.cpp:44-46.
+ * Performs the D2H copy the reference only does inside visualize() (.cpp:52) and
+ * synchronises the stream.  Pinned memory owned by the handle. */
+const float *jbf_filtered_host(jbf_handle *h);
+
+/* cv::gpu::GpuMat JointBilateralFilter::getSmoothImage_Device() -- .cpp:47-49.
+ * Returns packed BGR (CV_8UC3 continuous, *step = 3*width) materialised from the
+ * internal u8x4 guide of the last jbf_process. */
+const uint8_t *jbf_smooth_device(jbf_handle *h, size_t *step);
+
+/* The internal u8x4 smoothed guide of the last process call and its pitch. */
+const uint8_t *jbf_guide4_device(jbf_handle *h, size_t *step);
+
+/* void Upsampling(float* depthlow_device, cv::gpu::GpuMat colorhigh_image) --
+ * declared but never implemented in the reference (JointBilateralFilter.h:14,
+ * MarkovRandomField.h:14); defined by SURVEY.md 8(d) config 3: low-res sample
+ * (xl,yl) sits at high-res pixel (floor((xl+.5)*W/wl), floor((yl+.5)*H/hl)), all
+ * other pixels are holes, then the Process formula runs at the handle's
+ * (high-res) size and radius.  The sparse image is never materialised in HBM as
+ * an input: the scatter happens while staging tiles. */
+int jbf_upsample(jbf_handle *h, const float *depth_lo_dev, int wl, int hl, const uint8_t *bgr_hi_dev,
+                 size_t bgr_step, float *out_hi_dev);
+
+/* Which kernel the handle selected: 0 = register-tiled fast path, 1 = generic path
+ * (exotic sigmas / radius), bit 8 set when tiles are staged by TMA. */
+int jbf_kernel_variant(jbf_handle *h);
+
+/* "Next" row f1: MarkovRandomField::Process (MarkovRandomField.cu:4-49), raw guide. */
+int jbf_mrf(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step,
+            float *out_dev, int window_radius, float color_sigma, float smooth_sigma);
+
+/* "Next" row f3: DimensionConvertor::projectiveToReal(float*, float3*)
+ * (DimensionConvertor.cu:3-23, DimensionConvertor.h:34-61); cx, cy truncated to
+ * int as DimensionConvertor.cpp:8-9 does. */
+int kdme_projective_to_real(const float *depth_dev, float *xyz_dev, int width, int height, float fx,
+                            float fy, int cx, int cy, void *stream);
+
+/* ================= EdgeRefinedSuperpixel::depthmap_enhancement ============ */
+/* The guided cross-bilateral stage reached from TOFDepthInterpolation.cpp:65 ->
+ * EdgeRefinedSuperpixel::EdgeRefining (EdgeRefinedSuperpixel.cu:208-223) ->
+ * depthmap_enhancement (:104-205), with race-free read-input/write-output
+ * semantics.  labels_dev may be NULL (one label).  Reference constants
+ * (EdgeRefinedSuperpixel.cpp:4-7): radius 3, sigma_s 30, sigma_c 50, sigma_d 70.
+ * The guide is the RAW colour image (no pre-smooth). */
+int kdme_guided_fill(const float *depth_dev, const int32_t *labels_dev, const uint8_t *bgr_dev,
+                     size_t bgr_step, float *out_dev, int width, int height, int window_radius,
+                     float sigma_spatial, float sigma_color, float sigma_depth, void *stream);
+
+/* ========================= ArrayBuffer / Buffer2D ========================= */
+typedef struct buf2d_handle buf2d_handle;
+
+/* Buffer2D::Buffer2D(int width,int height) -- Buffer2D.cpp:4-10, ArrayBuffer.cpp:3-17:
+ * allocates width*height weighted_d {float d; float w;} (ArrayBuffer.h:12-15) and zeroes it
+ * (initDeviceMemoryElementsKernel, ArrayBuffer.cu:9-22). */
+int buf2d_create(buf2d_handle **out, int width, int height, int device, void *stream);
+void buf2d_destroy(buf2d_handle *b);
+/* ArrayBuffer::initDeviceMemoryElements -- ArrayBuffer.cu:27-30 */
+int buf2d_init(buf2d_handle *b);
+/* Buffer2D::insertData(float*) -- Buffer2D.cu:33-56: d = data, w = 1 */
+int buf2d_insert_f32(buf2d_handle *b, const float *data_dev);
+/* Buffer2D::insertData(weighted_d*) -- Buffer2D.cpp:13-15: D2D copy of the AoS */
+int buf2d_insert_dw(buf2d_handle *b, const float *dw_dev);
+/* Buffer2D::insertData(float2*) -- Buffer2D.cu:123-147: d = data.x, w = ROW INDEX
+ * (reference behaviour, Buffer2D.cu:137, reproduced and documented). */
+int buf2d_insert_f32x2(buf2d_handle *b, const float *xy_dev);
+/* Buffer2D::updateData(float*) -- Buffer2D.cu:97-120 -> updateWaitedDepth :13-30 */
+int buf2d_update_f32(buf2d_handle *b, const float *data_dev);
+/* n_frames successive updateData calls fused into one pass over the buffer
+ * (the 1000-frame averaging loop, main.cpp:86-101); frames are back to back. */
+int buf2d_update_batch_f32(buf2d_handle *b, const float *data_dev, int n_frames);
+/* Buffer2D::insertData(xn::DepthMetaData*) -- Buffer2D.cpp:18-32, without OpenNI:
+ * a HOST uint16 depth map (XnDepthPixel) is converted to float, uploaded and passed
+ * to updateData.  Synchronous. */
+int buf2d_update_u16_host(buf2d_handle *b, const uint16_t *depth_host);
+/* Buffer2D::getDepthMap / getWeightMap -- Buffer2D.cu:59-77, 79-94 */
+int buf2d_get_depth(buf2d_handle *b, float *out_dev);
+int buf2d_get_weight(buf2d_handle *b, float *out_dev);
+/* ArrayBuffer::getRawPointer -- ArrayBuffer.cpp:19-21 (borrowed; {d,w} interleaved) */
+float *buf2d_raw(buf2d_handle *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDME_B200_H */

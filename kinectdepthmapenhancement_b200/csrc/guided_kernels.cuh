@@ -1,0 +1,200 @@
+// guided_kernels.cuh -- label-guided cross-bilateral fill (depthmap_enhancement) and
+// the MRF filter, for sm_100a.
+//
+// guided_fill_kernel follows EdgeRefinedSuperpixel/EdgeRefinedSuperpixel.cu:104-205
+// (reached from TOFDepthInterpolation.cpp:65 via EdgeRefining, :208-223) with
+// race-free semantics: it reads `depth` and writes `out` (the reference overwrites
+// its input while neighbouring threads still read it).  Three sweeps of the window:
+//   1. same-label weighted mean (spatial x colour),
+//   2. mean absolute deviation of the same taps,
+//   3. all valid taps, colour sigma MUTATED PER VALID TAP (:170-176) and depth term
+//      centred on the sweep-1 mean.
+// The per-tap sigma recurrence is sequential in tap order, so one thread owns one
+// pixel and walks the taps in the reference's order; the tile + halo is staged in
+// shared memory once.  Weights are evaluated as one ex2 of summed log2-domain terms
+// with the reference's skip-if-zero guards made explicit.
+//
+// mrf_kernel follows MarkovRandomField/MarkovRandomField.cu:4-40 (next row f1).
+#pragma once
+#include "common.cuh"
+
+namespace kdme {
+
+struct GuidedParams {
+    int width, height, radius;
+    const float* depth;
+    const int32_t* labels;  // nullable
+    const uint8_t* bgr;     // RAW guide, packed BGR
+    long long bgr_step;
+    float* out;
+    float sigma_c, sigma_d;
+    float spatial[31 * 31];  // the reference's fp32 LUT (EdgeRefinedSuperpixel.cpp:46-55)
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_constant__ GuidedParams p) {
+    constexpr int NT = TW * TH;
+    const int R = p.radius, WS = 2 * R + 1, SP = TW + 2 * R, SH = TH + 2 * R;
+    extern __shared__ __align__(16) uint8_t smem_gf[];
+    float* sD = reinterpret_cast<float*>(smem_gf);
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sD + SP * SH);
+    int32_t* sLab = reinterpret_cast<int32_t*>(sG + SP * SH);
+    __shared__ float sL[31 * 31];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = x0 - R + sx, gy = y0 - R + sy;
+        bool in = (gx >= 0) & (gx < p.width) & (gy >= 0) & (gy < p.height);
+        float d = 0.f;
+        uint32_t g = 0u;
+        int32_t l = 0;
+        if (in) {
+            const long long k = (long long)gy * p.width + gx;
+            d = __ldg(p.depth + k);
+            const uint8_t* q = p.bgr + (long long)gy * p.bgr_step + 3 * gx;
+            g = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+            if (p.labels) l = __ldg(p.labels + k);
+        }
+        sD[idx] = (d > kValidDepth) ? d : 0.f;  // 0 marks "not a sample" (also out of bounds)
+        sG[idx] = g;
+        sLab[idx] = l;
+    }
+    for (int idx = tid; idx < WS * WS; idx += NT) {
+        const float s = p.spatial[idx];
+        sL[idx] = (s != 0.0f) ? log2f(s) : 0.0f;  // skip-if-zero guard (:129-130, :185-186)
+    }
+    __syncthreads();
+
+    const int lx = tid % TW, ly = tid / TW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= p.width || gy >= p.height) return;
+    const int pc = (ly + R) * SP + lx + R;
+    const uint32_t gpix = sG[pc];
+    const int32_t lp = sLab[pc];
+    const float kZero = -(float)kExpZeroArg;
+    const float l2e = (float)kLog2e;
+    const float sc0 = p.sigma_c;
+    const float den0 = 2 * (sc0 * sc0);
+
+    // accumulation origin: first sample in the window (keeps fp32 sums small)
+    float d0 = 0.f;
+    for (int t = 0; t < WS * WS && d0 == 0.f; ++t) {
+        const int i = t / WS, j = t - i * WS;
+        d0 = sD[(ly + i) * SP + lx + j];
+    }
+
+    // ---- sweep 1: same-label weighted mean (:116-139)
+    float acc = 0.f, wsum = 0.f;
+    for (int i = 0; i < WS; ++i)
+        for (int j = 0; j < WS; ++j) {
+            const int q = (ly + i) * SP + lx + j;
+            const float d = sD[q];
+            if (d == 0.f || sLab[q] != lp) continue;
+            const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+            const float cd = (float)__dp4a(ad, ad, 0u);
+            float lg = sL[i * WS + j] + kWeightBias;
+            if (sc0 != 0.0f) {
+                const float a = -cd / den0;
+                if (a >= kZero) lg = fmaf(a, l2e, lg);
+            }
+            const float f = ex2_approx(lg);
+            acc = fmaf(f, d - d0, acc);
+            wsum += f;
+        }
+    float o = 0.f;
+    if (wsum > 0.f) {
+        const float delta = acc / wsum;   // mean = d0 + delta
+        const float mean = d0 + delta;    // the reference's fp32 w_average
+        // ---- sweep 2: mean absolute deviation of the same taps (:143-156)
+        float dev = 0.f;
+        int count = 0;
+        for (int i = 0; i < WS; ++i)
+            for (int j = 0; j < WS; ++j) {
+                const int q = (ly + i) * SP + lx + j;
+                const float d = sD[q];
+                if (d == 0.f || sLab[q] != lp) continue;
+                dev += fabsf((d - d0) - delta);
+                count++;
+            }
+        if (count != 0) dev /= (float)count;
+        // 5.0*deviation/pow(w_average,2.0f): double expression, fp32 square (:171)
+        const float adaptive = (float)(5.0 * (double)dev / (double)(mean * mean));
+        // ---- sweep 3: all samples, mutating colour sigma (:158-195)
+        const float sq = (p.sigma_d != 0.0f) ? sqrtf(l2e / (2.0f * p.sigma_d * p.sigma_d)) : 0.f;
+        const float e_thr = (float)1.2247448713915890e1;  // sqrt(150)
+        float sigma = sc0;
+        float num = 0.f, den = 0.f;
+        bool poisoned = false;
+        for (int i = 0; i < WS; ++i)
+            for (int j = 0; j < WS; ++j) {
+                const int q = (ly + i) * SP + lx + j;
+                const float d = sD[q];
+                if (d == 0.f) continue;
+                const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+                const float cd = (float)__dp4a(ad, ad, 0u);
+                float lg = sL[i * WS + j] + kWeightBias;
+                if (sigma != 0.0f) {
+                    if (adaptive > sigma * 0.3f) sigma = adaptive; else sigma *= 0.3f;
+                    const float dn = 2 * (sigma * sigma);
+                    const float a = -cd / dn;          // -0/0 = NaN when sigma^2 underflowed and cd == 0
+                    if (a != a) poisoned = true;       // expf(NaN) = NaN != 0 -> filter *= NaN
+                    else if (a >= kZero) lg = fmaf(a, l2e, lg);
+                }
+                const float e = (d - d0) - delta;
+                const float es = e * sq;
+                if (p.sigma_d != 0.0f && !(fabsf(es) > e_thr)) lg = fmaf(-es, es, lg);
+                const float f = ex2_approx(lg);
+                num = fmaf(f, e, num);
+                den += f;
+            }
+        if (poisoned) o = __int_as_float(0x7fc00000);
+        else o = (den == 0.0f) ? 0.0f : mean + num / den;
+    }
+    p.out[(long long)gy * p.width + gx] = o;
+}
+
+// MarkovRandomField.cu:4-40: out = (d_p + sum f d_q) / (1 + sum f), f = smooth * expf(-sigma_c * cd)
+// over valid taps; evaluated as d_p + sum f (d_q - d_p) / (1 + sum f).
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW * TH)
+mrf_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ guide4, int guide_pitch,
+           float* __restrict__ out, int width, int height, int R, float color_sigma, float smooth_sigma) {
+    constexpr int NT = TW * TH;
+    const int WS = 2 * R + 1, SP = TW + 2 * R, SH = TH + 2 * R;
+    extern __shared__ __align__(16) uint8_t smem_mrf[];
+    float* sD = reinterpret_cast<float*>(smem_mrf);
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sD + SP * SH);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = x0 - R + sx, gy = y0 - R + sy;
+        bool in = (gx >= 0) & (gx < width) & (gy >= 0) & (gy < height);
+        sD[idx] = in ? __ldg(depth + (long long)gy * width + gx) : 0.f;
+        sG[idx] = in ? __ldg(guide4 + (long long)gy * guide_pitch + gx) : 0u;
+    }
+    __syncthreads();
+    const int lx = tid % TW, ly = tid / TW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= width || gy >= height) return;
+    const int pc = (ly + R) * SP + lx + R;
+    const uint32_t gpix = sG[pc];
+    const float dp = sD[pc];
+    const float nk = -color_sigma * (float)kLog2e;
+    float num = 0.f, den = 1.0f;
+    for (int i = 0; i < WS; ++i)
+        for (int j = 0; j < WS; ++j) {
+            const int q = (ly + i) * SP + lx + j;
+            const float d = sD[q];
+            if (!(d > kValidDepth)) continue;
+            const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+            const float cd = (float)__dp4a(ad, ad, 0u);
+            const float f = (color_sigma != 0.0f) ? smooth_sigma * ex2_approx(cd * nk) : 0.f;
+            num = fmaf(f, d - dp, num);
+            den += f;
+        }
+    out[(long long)gy * width + gx] = (den == 0.0f) ? 0.0f : dp + num / den;
+}
+
+}  // namespace kdme

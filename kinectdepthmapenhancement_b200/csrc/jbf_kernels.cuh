@@ -1,0 +1,404 @@
+// jbf_kernels.cuh -- two-pass joint bilateral depth filter for sm_100a.
+//
+// Computes what joint_bilateral_filtering computes (reference:
+// JointBilateralFilter/JointBilateralFilter.cu:4-83) for every pixel of every
+// frame, but organised for Blackwell:
+//
+//   * one CTA = one TW x TH output tile; the depth tile and the smoothed-guide
+//     tile, each with its radius-r halo, are staged into shared memory by TMA
+//     (cp.async.bulk.tensor, zero fill outside the image == the reference's
+//     bounds test, .cu:21) -- or by plain coalesced loads when the frame pitch
+//     is not 16-byte aligned, or by an on-the-fly low-res scatter (Upsampling);
+//   * a prepare step rewrites the staged depth as (d - d_ref) * sqrt(log2e/2sd^2)
+//     (d_ref = smallest valid depth of the staged tile) and emits one "magic"
+//     word per staged pixel that carries validity (d > 50);
+//   * each thread owns 4 horizontally adjacent pixels and sweeps the window row
+//     by row; a staged row segment is fetched once with 16-byte LDS and reused
+//     by all 4 pixels (4*(2r+1) taps per 2r+4 fetched columns);
+//   * a tap costs: VABSDIFF4 + IDP.4A (exact integer colour distance, validity
+//     folded in through the accumulator) + FADD + FFMA (spatial-LUT row entry
+//     + colour term) [+ FADD, FSETP, predicated FFMA for the depth-range term
+//     in pass 2] + ONE MUFU.EX2 + FFMA + FADD.  No expf, no division, no
+//     branch per tap;
+//   * sums are accumulated around local origins (tile d_ref, per-thread d0,
+//     per-pixel pass-1 mean), which is what makes fp32 agree with the fp64
+//     evaluation of the reference formula to ~1 ulp of the output.
+//
+// The reference's quirks are kept: > 50 validity, hole filling (centre need not
+// be valid), skip-if-zero guards (spatial: folded into the LUT; colour: cannot
+// fire on this path, the host routes such sigmas to the generic kernel; depth:
+// explicit |e| > sqrt(150) compare), two passes with the range term centred on
+// the pass-1 mean.
+#pragma once
+#include "common.cuh"
+
+namespace kdme {
+
+enum StageMode : int { kStagePlain = 0, kStageTma = 1, kStageUpsample = 2 };
+
+struct JbfParams {
+    int width, height, n_frames;
+    const float* depth;          // [n][H][W]                      (plain / TMA)
+    const uint32_t* guide4;      // [n][H][guide_pitch] u8x4 BGR0  (smoothed guide)
+    float* out;                  // [n][H][W]
+    long long depth_frame_stride;   // elements
+    long long guide_frame_stride;   // words
+    int guide_pitch;                // words per row
+    const float* ltab;           // [(2r+1)][LP]: log2(S_ij)+bias, or bias where S_ij == 0
+    float nkc;                   // -log2e / (2 sigma_c^2)
+    float sq, inv_sq;            // depth scale sqrt(log2e/(2 sigma_d^2)) and inverse
+    float e_thr;                 // sqrt(150): scaled |d - m| beyond which fp32 expf() == 0
+    int mode;                    // StageMode
+    const float* depth_lo;       // upsample: low-res depth [hl][wl]
+    int wl, hl;
+};
+
+template <int R, int TW, int TH>
+struct JbfTile {
+    static constexpr int WS = 2 * R + 1;
+    static constexpr int RP = (R + 3) & ~3;        // halo columns rounded up to a 16-byte multiple
+    static constexpr int SP = TW + 2 * RP;         // staged row pitch (words)
+    static constexpr int SH = TH + 2 * R;          // staged rows
+    static constexpr int LP = (WS + 3) & ~3;       // LUT row pitch
+    static constexpr int NT = (TW / 4) * TH;       // threads per CTA
+    static constexpr int NW = 2 * RP + 4;          // words fetched per row per thread
+    static constexpr int C0 = RP - R;              // first used column of the fetched segment
+    static constexpr int PLANE = ((SP * SH * 4 + 127) / 128) * 128;
+    static constexpr int LBYTES = ((WS * LP * 4 + 127) / 128) * 128;
+    static constexpr int SMEM = 3 * PLANE + LBYTES + 128;
+};
+
+// low-res sample index landing on high-res coordinate x, or -1:
+// x_hi(xl) = floor((2 xl + 1) * W / (2 wl)); at most one xl per x when W >= wl.
+__device__ __forceinline__ int upsample_site(int x, int W, int wl) {
+    long long num = 2LL * wl * x - W;
+    int xl = (num <= 0) ? 0 : (int)((num + 2LL * W - 1) / (2LL * W));
+    if (xl >= wl) return -1;
+    return ((int)(((2LL * xl + 1) * W) / (2LL * wl)) == x) ? xl : -1;
+}
+
+template <int R, int TW, int TH, int MINB>
+__global__ void __launch_bounds__((TW / 4) * TH, MINB)
+jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_constant__ CUtensorMap tm_guide,
+                const JbfParams p) {
+    using T = JbfTile<R, TW, TH>;
+    constexpr int WS = T::WS, RP = T::RP, SP = T::SP, SH = T::SH, LP = T::LP, NT = T::NT, NW = T::NW, C0 = T::C0;
+
+    extern __shared__ __align__(128) uint8_t smem_fast[];
+    float* sD = reinterpret_cast<float*>(smem_fast);
+    uint32_t* sG = reinterpret_cast<uint32_t*>(smem_fast + T::PLANE);
+    uint32_t* sM = reinterpret_cast<uint32_t*>(smem_fast + 2 * T::PLANE);
+    float* sL = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_fast + 3 * T::PLANE + T::LBYTES);
+    float* sRed = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE + T::LBYTES + 16);  // NT/32 <= 16 floats
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const int sx0 = x0 - RP, sy0 = y0 - R;  // image coords of staged (0,0)
+
+    // ---------------- stage A: raw depth + guide tile with halo -> shared memory
+    if (p.mode == kStageTma) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, 2u * SP * SH * 4u);
+            tma_load_3d(sD, &tm_depth, bar, sx0, sy0, frame);
+            tma_load_3d(sG, &tm_guide, bar, sx0, sy0, frame);
+        }
+    } else {
+        const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
+        const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
+        for (int idx = tid; idx < SP * SH; idx += NT) {
+            int sy = idx / SP, sx = idx - sy * SP;
+            int gx = sx0 + sx, gy = sy0 + sy;
+            bool in = (gx >= 0) & (gx < p.width) & (gy >= 0) & (gy < p.height);
+            float d = 0.f;
+            uint32_t g = 0u;
+            if (in) {
+                g = __ldg(gsrc + (long long)gy * p.guide_pitch + gx);
+                if (p.mode == kStagePlain) {
+                    d = __ldg(dsrc + (long long)gy * p.width + gx);
+                } else {  // upsample: scatter the low-res sample onto its high-res site
+                    int xl = upsample_site(gx, p.width, p.wl);
+                    int yl = upsample_site(gy, p.height, p.hl);
+                    if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
+                }
+            }
+            sD[idx] = d;
+            sG[idx] = g;
+        }
+    }
+    // spatial LUT rows (log2 domain, bias folded in)
+    for (int idx = tid; idx < WS * LP; idx += NT) sL[idx] = __ldg(p.ltab + idx);
+    if (p.mode == kStageTma) mbar_wait(bar, 0);
+    __syncthreads();
+
+    // ---------------- stage B: validity, tile origin d_ref, scaled/shifted depth
+    float lmin = 3.0e38f;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        float d = sD[idx];
+        if (d > kValidDepth) lmin = fminf(lmin, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    if ((tid & 31) == 0) sRed[tid >> 5] = lmin;
+    __syncthreads();
+    float dref = 3.0e38f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) dref = fminf(dref, sRed[w]);
+    if (dref > 1.0e38f) dref = 0.f;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        float d = sD[idx];
+        bool v = d > kValidDepth;
+        sD[idx] = v ? (d - dref) * p.sq : 0.f;
+        sM[idx] = v ? kMagicValid : kMagicInvalid;
+    }
+    __syncthreads();
+
+    // ---------------- compute: 4 pixels per thread
+    const int lx = tid % (TW / 4), ly = tid / (TW / 4);
+    const int colbase = 4 * lx;  // staged column of the fetched segment's first word
+    uint32_t gp[4];
+    float d0 = 0.f;
+    {
+        const int c = (ly + R) * SP + RP + colbase;
+        const uint4 g4 = *reinterpret_cast<const uint4*>(sG + c);
+        const float4 d4 = *reinterpret_cast<const float4*>(sD + c);
+        const uint4 m4 = *reinterpret_cast<const uint4*>(sM + c);
+        gp[0] = g4.x; gp[1] = g4.y; gp[2] = g4.z; gp[3] = g4.w;
+        // per-thread accumulation origin: first valid own pixel (scaled, tile-relative)
+        d0 = (m4.x == kMagicValid) ? d4.x
+           : (m4.y == kMagicValid) ? d4.y
+           : (m4.z == kMagicValid) ? d4.z
+           : (m4.w == kMagicValid) ? d4.w : 0.f;
+    }
+    const float nkc = p.nkc;
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int i = 0; i < WS; ++i) {
+        const int rowoff = (ly + i) * SP + colbase;
+        uint32_t gq[NW], mq[NW];
+        float dq[NW], L[LP];
+#pragma unroll
+        for (int v = 0; v < NW / 4; ++v) {
+            const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
+            const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
+            const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
+            gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
+            dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
+            mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
+        }
+#pragma unroll
+        for (int v = 0; v < LP / 4; ++v) {
+            const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
+            L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
+        }
+#pragma unroll
+        for (int c = C0; c < C0 + WS + 3; ++c) {
+            const float dsh = dq[c] - d0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = c - C0 - k;
+                if (j >= 0 && j < WS) {
+                    const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
+                    const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
+                    const float f = ex2_approx(fmaf(cdf, nkc, L[j]));
+                    acc[k] = fmaf(f, dsh, acc[k]);
+                    wsum[k] += f;
+                }
+            }
+        }
+    }
+
+    // pass-1 weighted mean, in scaled tile-relative units
+    float m[4];
+    bool any[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        any[k] = wsum[k] > 0.f;
+        m[k] = any[k] ? (acc[k] / wsum[k] + d0) : 0.f;
+    }
+
+    const float e_thr = p.e_thr;
+    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int i = 0; i < WS; ++i) {
+        const int rowoff = (ly + i) * SP + colbase;
+        uint32_t gq[NW], mq[NW];
+        float dq[NW], L[LP];
+#pragma unroll
+        for (int v = 0; v < NW / 4; ++v) {
+            const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
+            const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
+            const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
+            gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
+            dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
+            mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
+        }
+#pragma unroll
+        for (int v = 0; v < LP / 4; ++v) {
+            const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
+            L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
+        }
+#pragma unroll
+        for (int c = C0; c < C0 + WS + 3; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = c - C0 - k;
+                if (j >= 0 && j < WS) {
+                    const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
+                    const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
+                    float arg = fmaf(cdf, nkc, L[j]);
+                    const float e = dq[c] - m[k];
+                    // fp32 expf(-(d-m)^2/(2 sd^2)) == 0  <=>  factor skipped (.cu:67-68)
+                    if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
+                    const float f = ex2_approx(arg);
+                    num[k] = fmaf(f, e, num[k]);
+                    den[k] += f;
+                }
+            }
+        }
+    }
+
+    // ---------------- epilogue: back to millimetres, 16-byte store
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // den > 0 whenever any tap is valid (weights are biased into the normal range)
+        const float r = (m[k] + num[k] / den[k]) * p.inv_sq;
+        o[k] = any[k] ? (dref + r) : 0.f;
+    }
+    const int gy = y0 + ly, gx = x0 + 4 * lx;
+    if (gy < p.height && gx < p.width) {
+        float* dst = p.out + (long long)frame * p.width * p.height + (long long)gy * p.width + gx;
+        if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            stg_stream_f4(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (gx + k < p.width) dst[k] = o[k];
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------
+// Generic kernel: any radius <= KDME_MAX_RADIUS, any sigmas (including those for
+// which the colour skip-if-zero guard can fire, sigma_c == 0 and sigma_d == 0).
+// One pixel per thread, same staging and the same shifted accumulation; the
+// guards are evaluated explicitly per tap.  Used when the fast path's
+// preconditions do not hold; slower by design.
+struct JbfGenericParams {
+    JbfParams base;
+    int radius;
+    int cd_skip;      // colour factor skipped when cd > cd_skip (fp32 expf == 0); INT_MAX = never
+    int use_color;    // 0 when sigma_c == 0 (factor is 0 -> skipped, .cu:26-27,32-33)
+    int use_depth;    // 0 when sigma_d == 0 (depth_filter uninitialised in the reference -> skipped)
+};
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW * TH)
+jbf_generic_kernel(const JbfGenericParams gp_) {
+    const JbfParams& p = gp_.base;
+    const int R = gp_.radius, WS = 2 * R + 1;
+    const int SP = TW + 2 * R, SH = TH + 2 * R;
+    extern __shared__ __align__(128) uint8_t smem_gen[];
+    float* sD = reinterpret_cast<float*>(smem_gen);
+    uint32_t* sG = reinterpret_cast<uint32_t*>(sD + SP * SH);
+    float* sL = reinterpret_cast<float*>(sG + SP * SH);
+    __shared__ float sRed[32];
+    constexpr int NT = TW * TH;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
+    const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = x0 - R + sx, gy = y0 - R + sy;
+        bool in = (gx >= 0) & (gx < p.width) & (gy >= 0) & (gy < p.height);
+        float d = 0.f;
+        uint32_t g = 0u;
+        if (in) {
+            g = __ldg(gsrc + (long long)gy * p.guide_pitch + gx);
+            if (p.mode == kStageUpsample) {
+                int xl = upsample_site(gx, p.width, p.wl);
+                int yl = upsample_site(gy, p.height, p.hl);
+                if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
+            } else {
+                d = __ldg(dsrc + (long long)gy * p.width + gx);
+            }
+        }
+        sD[idx] = d;
+        sG[idx] = g;
+    }
+    for (int idx = tid; idx < WS * WS; idx += NT) sL[idx] = __ldg(p.ltab + idx);
+    __syncthreads();
+    float lmin = 3.0e38f;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        float d = sD[idx];
+        if (d > kValidDepth) lmin = fminf(lmin, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    if ((tid & 31) == 0) sRed[tid >> 5] = lmin;
+    __syncthreads();
+    float dref = 3.0e38f;
+    for (int w = 0; w < NT / 32; ++w) dref = fminf(dref, sRed[w]);
+    if (dref > 1.0e38f) dref = 0.f;
+    __syncthreads();
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        float d = sD[idx];
+        // invalid samples are flagged with NaN-free sentinel: negative infinity never occurs in input
+        sD[idx] = (d > kValidDepth) ? (d - dref) * p.sq : -3.0e38f;
+    }
+    __syncthreads();
+
+    const int lx = tid % TW, ly = tid / TW;
+    const int pc = (ly + R) * SP + lx + R;
+    const uint32_t gpix = sG[pc];
+    const float dc = sD[pc];
+    const float d0 = (dc > -1.0e38f) ? dc : 0.f;
+    float acc = 0.f, wsum = 0.f;
+    for (int i = 0; i < WS; ++i)
+        for (int j = 0; j < WS; ++j) {
+            const int q = (ly + i) * SP + lx + j;
+            const float d = sD[q];
+            if (!(d > -1.0e38f)) continue;
+            const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+            const int cd = (int)__dp4a(ad, ad, 0u);
+            float arg = sL[i * WS + j];
+            if (gp_.use_color && cd <= gp_.cd_skip) arg = fmaf((float)cd, p.nkc, arg);
+            const float f = ex2_approx(arg);
+            acc = fmaf(f, d - d0, acc);
+            wsum += f;
+        }
+    float o = 0.f;
+    if (wsum > 0.f) {
+        const float m = acc / wsum + d0;
+        float num = 0.f, den = 0.f;
+        for (int i = 0; i < WS; ++i)
+            for (int j = 0; j < WS; ++j) {
+                const int q = (ly + i) * SP + lx + j;
+                const float d = sD[q];
+                if (!(d > -1.0e38f)) continue;
+                const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+                const int cd = (int)__dp4a(ad, ad, 0u);
+                float arg = sL[i * WS + j];
+                if (gp_.use_color && cd <= gp_.cd_skip) arg = fmaf((float)cd, p.nkc, arg);
+                const float e = d - m;
+                if (gp_.use_depth && !(fabsf(e) > p.e_thr)) arg = fmaf(-e, e, arg);
+                const float f = ex2_approx(arg);
+                num = fmaf(f, e, num);
+                den += f;
+            }
+        o = (den > 0.f) ? dref + (m + num / den) * p.inv_sq : 0.f;
+    }
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx < p.width && gy < p.height)
+        p.out[(long long)frame * p.width * p.height + (long long)gy * p.width + gx] = o;
+}
+
+}  // namespace kdme

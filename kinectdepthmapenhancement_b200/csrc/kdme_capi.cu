@@ -1,0 +1,710 @@
+// kdme_capi.cu -- extern "C" boundary (include/kdme_b200.h) over the sm_100a kernels.
+//
+// Host-side logic only: argument validation, LUT construction (the reference's
+// calcSpatialFilter, JointBilateralFilter.cpp:31-40), kernel selection, TMA
+// descriptor encoding, launch.  There is no CPU fallback: every entry point
+// either launches a CUDA kernel or returns an error.
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kdme_b200.h"
+#include "buffer2d_kernels.cuh"
+#include "guided_kernels.cuh"
+#include "jbf_kernels.cuh"
+#include "presmooth_kernels.cuh"
+
+using namespace kdme;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(-(int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+extern "C" const char* kdme_last_error(void) { return g_err.c_str(); }
+extern "C" const char* kdme_version(void) { return "kdme_b200 0.1.0 sm_100a"; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D map over [n][rows][pitch_elems] 4-byte elements, box {bx, by, 1}, zero OOB fill.
+static bool encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int width, int height, int n,
+                       long long row_pitch_bytes, long long frame_pitch_bytes, int bx, int by) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)row_pitch_bytes, (cuuint64_t)frame_pitch_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------ JBF handle
+struct jbf_handle {
+    int width = 0, height = 0, radius = 0, max_batch = 1, device = 0;
+    float sigma_s = 0, sigma_c = 0, sigma_d = 0;
+    cudaStream_t stream = nullptr;
+    // pre-smooth (JointBilateralFilter.cu:285)
+    int ps_ksize = 5;
+    float ps_sigma_c = 30.f, ps_sigma_s = 30.f;
+    float *ps_space_dev = nullptr, *ps_color_dev = nullptr;
+    // owned buffers
+    float* filtered_dev = nullptr;   // Filtered_Device
+    float* filtered_host = nullptr;  // Filtered_Host (pinned, lazy)
+    uint32_t* guide4 = nullptr;      // smooth_Device in the internal u8x4 layout, max_batch frames
+    int guide_pitch = 0;             // words
+    uint8_t* smooth_bgr = nullptr;   // packed copy for getSmoothImage_Device (lazy)
+    float* ltab_dev = nullptr;       // fast layout [WS][LP]
+    float* ltab_generic_dev = nullptr;  // [WS][WS]
+    // derived
+    bool fast = false;
+    float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
+    int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
+    bool force_no_tma = false;
+    int last_variant = 0;
+    // host pipeline (jbf_process_host)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    float* pipe_depth[2] = {nullptr, nullptr};
+    uint8_t* pipe_bgr[2] = {nullptr, nullptr};
+    float* pipe_out[2] = {nullptr, nullptr};
+    size_t pipe_bgr_step = 0;
+};
+
+static bool fast_radius_available(int r);
+
+// calcSpatialFilter -- JointBilateralFilter.cpp:31-40, fp32 on the host as the reference does.
+static void host_spatial_lut(std::vector<float>& lut, int ws, float sigma_s) {
+    lut.resize((size_t)ws * ws);
+    for (int i = 0; i < ws; i++)
+        for (int j = 0; j < ws; j++) {
+            float dx = (float)(j - ws / 2), dy = (float)(i - ws / 2);
+            float dis_x = dx * dx, dis_y = dy * dy;
+            lut[(size_t)i * ws + j] = expf(-(dis_x + dis_y) / (2.0f * (sigma_s * sigma_s)));
+        }
+}
+
+static int build_tables(jbf_handle* h) {
+    const int ws = 2 * h->radius + 1, lp = (ws + 3) & ~3;
+    std::vector<float> lut;
+    host_spatial_lut(lut, ws, h->sigma_s);
+    std::vector<float> lf((size_t)ws * lp, 0.f), lg((size_t)ws * ws, 0.f);
+    for (int i = 0; i < ws; i++)
+        for (int j = 0; j < ws; j++) {
+            float s = lut[(size_t)i * ws + j];
+            // skip-if-zero guard on the spatial factor (JointBilateralFilter.cu:30-31,63-64)
+            float l = (s != 0.0f && std::isfinite(s)) ? (float)(std::log2((double)s) + (double)kWeightBias)
+                                                       : kWeightBias;
+            lf[(size_t)i * lp + j] = l;
+            lg[(size_t)i * ws + j] = l;
+        }
+    CK(cudaMalloc(&h->ltab_dev, lf.size() * sizeof(float)));
+    CK(cudaMalloc(&h->ltab_generic_dev, lg.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->ltab_dev, lf.data(), lf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ltab_generic_dev, lg.data(), lg.size() * sizeof(float), cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    // colour factor: exp(-cd/(2 sc^2)); cd is an integer in [0, 3*255^2]
+    h->use_color = (h->sigma_c != 0.0f);
+    h->use_depth = (h->sigma_d != 0.0f);
+    h->cd_skip = INT_MAX;
+    if (h->use_color) {
+        const float den = 2 * (h->sigma_c * h->sigma_c);
+        h->nkc = (float)(-kLog2e / (2.0 * (double)h->sigma_c * (double)h->sigma_c));
+        // largest cd whose fp32 expf() is still non-zero (monotone): binary search
+        int lo = 0, hi = 3 * 255 * 255;
+        if (expf(-(float)hi / den) == 0.0f) {
+            while (lo < hi) {
+                int mid = (lo + hi + 1) / 2;
+                if (expf(-(float)mid / den) != 0.0f) lo = mid; else hi = mid - 1;
+            }
+            h->cd_skip = lo;
+        }
+    } else {
+        h->nkc = 0.f;
+    }
+    if (h->use_depth) {
+        const double k = kLog2e / (2.0 * (double)h->sigma_d * (double)h->sigma_d);
+        h->sq = (float)std::sqrt(k);
+        h->inv_sq = (float)(1.0 / std::sqrt(k));
+        h->e_thr = (float)std::sqrt(kExpZeroArg * kLog2e);  // == sqrt(150) in scaled units
+    } else {
+        h->sq = 1.f; h->inv_sq = 1.f; h->e_thr = 3.0e38f;
+    }
+    // fast path: colour guard can never fire, all factors present, kernel instantiated, and the
+    // invalid-tap marker (1.7e38 * nkc) must still drive the exponent to -inf.
+    h->fast = h->use_color && h->use_depth && h->cd_skip == INT_MAX && std::isfinite(h->nkc) &&
+              (h->nkc < -1e-20f) && std::isfinite(h->sq) && h->sq > 0.f && fast_radius_available(h->radius);
+    if (getenv("KDME_FORCE_GENERIC")) h->fast = false;
+    h->force_no_tma = getenv("KDME_NO_TMA") != nullptr;
+    return KDME_OK;
+}
+
+static int build_presmooth_luts(jbf_handle* h) {
+    if (h->ps_ksize == 0) return KDME_OK;
+    const int k = h->ps_ksize, r = k / 2;
+    std::vector<float> sp((size_t)k * k), col(766);
+    const float ss = -0.5f / (h->ps_sigma_s * h->ps_sigma_s);
+    const float sc = -0.5f / (h->ps_sigma_c * h->ps_sigma_c);
+    for (int dy = -r; dy <= r; dy++)
+        for (int dx = -r; dx <= r; dx++) {
+            int s2 = dx * dx + dy * dy;
+            sp[(size_t)(dy + r) * k + (dx + r)] = (s2 > r * r) ? -1.0f : expf((float)s2 * ss);
+        }
+    for (int n = 0; n <= 765; n++) col[n] = expf((float)(n * n) * sc);
+    if (!h->ps_space_dev) CK(cudaMalloc(&h->ps_space_dev, kPsMaxK * kPsMaxK * sizeof(float)));
+    if (!h->ps_color_dev) CK(cudaMalloc(&h->ps_color_dev, 768 * sizeof(float)));
+    CK(cudaMemcpyAsync(h->ps_space_dev, sp.data(), sp.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ps_color_dev, col.data(), col.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDME_OK;
+}
+
+extern "C" int jbf_create(jbf_handle** out, int width, int height, float sigma_spatial, float sigma_color,
+                          float sigma_depth, int window_radius, int max_batch, int device, void* stream) {
+    if (!out) return fail(KDME_EINVAL, "jbf_create: out is NULL");
+    *out = nullptr;
+    if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "jbf_create: width/height must be positive");
+    if (window_radius < 0 || window_radius > KDME_MAX_RADIUS)
+        return fail(KDME_EINVAL, "jbf_create: window_radius must be in [0, 15]");
+    if (max_batch < 1) return fail(KDME_EINVAL, "jbf_create: max_batch must be >= 1");
+    if (!(sigma_spatial == sigma_spatial) || !(sigma_color == sigma_color) || !(sigma_depth == sigma_depth) ||
+        sigma_spatial < 0 || sigma_color < 0 || sigma_depth < 0)
+        return fail(KDME_EINVAL, "jbf_create: sigmas must be non-negative numbers");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(KDME_EINVAL, "jbf_create: no such CUDA device");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KDME_EINVAL, "jbf_create: cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(KDME_ENOTSUP, "jbf_create: this library is built for sm_100a (B200) only");
+    jbf_handle* h = new jbf_handle();
+    h->width = width; h->height = height; h->radius = window_radius; h->max_batch = max_batch;
+    h->device = device; h->stream = (cudaStream_t)stream;
+    h->sigma_s = sigma_spatial; h->sigma_c = sigma_color; h->sigma_d = sigma_depth;
+    h->guide_pitch = (width + 3) & ~3;
+    int rc = KDME_OK;
+    auto cleanup = [&](int code) { jbf_destroy(h); return code; };
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->filtered_dev, (size_t)width * height * sizeof(float))) != cudaSuccess)
+        return cleanup(fail(-(int)e, "jbf_create: cudaMalloc(Filtered_Device) failed"));
+    if ((e = cudaMalloc(&h->guide4, (size_t)max_batch * height * h->guide_pitch * sizeof(uint32_t))) != cudaSuccess)
+        return cleanup(fail(-(int)e, "jbf_create: cudaMalloc(smooth_Device) failed"));
+    if ((rc = build_tables(h)) != KDME_OK) return cleanup(rc);
+    if ((rc = build_presmooth_luts(h)) != KDME_OK) return cleanup(rc);
+    *out = h;
+    return KDME_OK;
+}
+
+extern "C" void jbf_destroy(jbf_handle* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    cudaFree(h->filtered_dev);
+    if (h->filtered_host) cudaFreeHost(h->filtered_host);
+    cudaFree(h->guide4);
+    cudaFree(h->smooth_bgr);
+    cudaFree(h->ltab_dev);
+    cudaFree(h->ltab_generic_dev);
+    cudaFree(h->ps_space_dev);
+    cudaFree(h->ps_color_dev);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(h->pipe_depth[b]); cudaFree(h->pipe_bgr[b]); cudaFree(h->pipe_out[b]);
+        if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
+        if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+        if (h->ev_free[b]) cudaEventDestroy(h->ev_free[b]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+extern "C" int jbf_set_presmooth(jbf_handle* h, int ksize, float sigma_color, float sigma_spatial) {
+    if (!h) return fail(KDME_EINVAL, "jbf_set_presmooth: NULL handle");
+    if (ksize != 0 && (ksize < 1 || ksize > kPsMaxK || (ksize & 1) == 0))
+        return fail(KDME_EINVAL, "jbf_set_presmooth: ksize must be 0 (off) or odd in [1, 9]");
+    if (ksize != 0 && (!(sigma_color > 0) || !(sigma_spatial > 0)))
+        return fail(KDME_EINVAL, "jbf_set_presmooth: sigmas must be positive");
+    DeviceGuard g(h->device);
+    h->ps_ksize = ksize; h->ps_sigma_c = sigma_color; h->ps_sigma_s = sigma_spatial;
+    return build_presmooth_luts(h);
+}
+
+// ------------------------------------------------------------------ launches
+static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, uint32_t* guide4, int guide_pitch,
+                            int n) {
+    if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
+    if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
+    if (h->ps_ksize == 0) {
+        dim3 blk(128), grd((h->width + 127) / 128, h->height, n);
+        bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr, (long long)bgr_step, (long long)bgr_step * h->height,
+                                                         guide4, guide_pitch, (long long)guide_pitch * h->height,
+                                                         h->width, h->height);
+    } else {
+        PresmoothParams p;
+        p.width = h->width; p.height = h->height; p.n_frames = n;
+        p.bgr = bgr; p.bgr_step = (long long)bgr_step; p.bgr_frame_stride = (long long)bgr_step * h->height;
+        p.guide4 = guide4; p.guide_pitch = guide_pitch; p.guide_frame_stride = (long long)guide_pitch * h->height;
+        p.ksize = h->ps_ksize; p.space_lut = h->ps_space_dev; p.color_lut = h->ps_color_dev;
+        constexpr int TW = 32, TH = 8;
+        dim3 grd((h->width + TW - 1) / TW, (h->height + TH - 1) / TH, n);
+        presmooth_kernel<TW, TH><<<grd, TW * TH, 0, h->stream>>>(p);
+    }
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+template <int R>
+static int launch_fast_r(jbf_handle* h, const JbfParams& p, const CUtensorMap& tmd, const CUtensorMap& tmg) {
+    constexpr int TW = 64, TH = 16, MINB = 2;
+    using T = JbfTile<R, TW, TH>;
+    auto kern = jbf_fast_kernel<R, TW, TH, MINB>;
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        attr_done[h->device & 63] = true;
+    }
+    dim3 grd((p.width + TW - 1) / TW, (p.height + TH - 1) / TH, p.n_frames);
+    kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+template <int R>
+static void tile_box(int& bx, int& by) {
+    using T = JbfTile<R, 64, 16>;
+    bx = T::SP; by = T::SH;
+}
+
+#define KDME_FAST_RADII(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)
+
+static bool fast_radius_available(int r) {
+    switch (r) {
+#define X(R) case R:
+        KDME_FAST_RADII(X)
+#undef X
+        return true;
+        default: return false;
+    }
+}
+
+static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guide4, int guide_pitch, float* out,
+                         int n, int mode, const float* depth_lo, int wl, int hl) {
+    JbfParams p;
+    p.width = h->width; p.height = h->height; p.n_frames = n;
+    p.depth = depth; p.guide4 = guide4; p.out = out;
+    p.depth_frame_stride = (long long)h->width * h->height;
+    p.guide_frame_stride = (long long)guide_pitch * h->height;
+    p.guide_pitch = guide_pitch;
+    p.nkc = h->nkc; p.sq = h->sq; p.inv_sq = h->inv_sq; p.e_thr = h->e_thr;
+    p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
+    if (h->fast) {
+        p.ltab = h->ltab_dev;
+        CUtensorMap tmd, tmg;
+        memset(&tmd, 0, sizeof(tmd)); memset(&tmg, 0, sizeof(tmg));
+        if (p.mode == kStagePlain && !h->force_no_tma && (h->width % 4 == 0) && (guide_pitch % 4 == 0) &&
+            ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) && ((reinterpret_cast<uintptr_t>(guide4) & 15) == 0)) {
+            int bx = 0, by = 0;
+            switch (h->radius) {
+#define X(R) case R: tile_box<R>(bx, by); break;
+                KDME_FAST_RADII(X)
+#undef X
+            }
+            bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, h->width, h->height, n,
+                                 (long long)h->width * 4, (long long)h->width * h->height * 4, bx, by) &&
+                      encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, guide4, h->width, h->height, n,
+                                 (long long)guide_pitch * 4, (long long)guide_pitch * h->height * 4, bx, by);
+            if (ok) p.mode = kStageTma;
+        }
+        h->last_variant = 0 | (p.mode == kStageTma ? 0x100 : 0);
+        switch (h->radius) {
+#define X(R) case R: return launch_fast_r<R>(h, p, tmd, tmg);
+            KDME_FAST_RADII(X)
+#undef X
+        }
+        return fail(KDME_ENOTSUP, "no fast kernel for this radius");
+    }
+    // generic path
+    JbfGenericParams gp;
+    gp.base = p;
+    gp.base.ltab = h->ltab_generic_dev;
+    gp.radius = h->radius; gp.cd_skip = h->cd_skip; gp.use_color = h->use_color; gp.use_depth = h->use_depth;
+    constexpr int TW = 32, TH = 8;
+    const int SP = TW + 2 * h->radius, SH = TH + 2 * h->radius, ws = 2 * h->radius + 1;
+    size_t smem = (size_t)SP * SH * 8 + (size_t)ws * ws * 4;
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        CK(cudaFuncSetAttribute(jbf_generic_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_done[h->device & 63] = true;
+    }
+    dim3 grd((p.width + TW - 1) / TW, (p.height + TH - 1) / TH, n);
+    jbf_generic_kernel<TW, TH><<<grd, TW * TH, smem, h->stream>>>(gp);
+    CK(cudaGetLastError());
+    h->last_variant = 1;
+    return KDME_OK;
+}
+
+extern "C" int jbf_presmooth(jbf_handle* h, const uint8_t* bgr_dev, size_t bgr_step, uint8_t* guide4_dev,
+                             size_t guide_step, int n_frames) {
+    if (!h || !bgr_dev || !guide4_dev) return fail(KDME_EINVAL, "jbf_presmooth: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_presmooth: n_frames must be >= 1");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_presmooth: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_presmooth(h, bgr_dev, bgr_step, reinterpret_cast<uint32_t*>(guide4_dev), (int)(guide_step / 4),
+                            n_frames);
+}
+
+extern "C" int jbf_filter_guide4(jbf_handle* h, const float* depth_dev, const uint8_t* guide4_dev, size_t guide_step,
+                                 float* out_dev, int n_frames) {
+    if (!h || !depth_dev || !guide4_dev || !out_dev) return fail(KDME_EINVAL, "jbf_filter_guide4: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_filter_guide4: n_frames must be >= 1");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_filter_guide4: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_filter(h, depth_dev, reinterpret_cast<const uint32_t*>(guide4_dev), (int)(guide_step / 4), out_dev,
+                         n_frames, kStagePlain, nullptr, 0, 0);
+}
+
+extern "C" int jbf_process_batch(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step,
+                                 float* out_dev, int n_frames) {
+    if (!h || !depth_dev || !bgr_dev || !out_dev) return fail(KDME_EINVAL, "jbf_process_batch: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_process_batch: n_frames must be >= 1");
+    if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
+    DeviceGuard g(h->device);
+    const size_t plane = (size_t)h->width * h->height;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+        const int n = (n_frames - f0 < h->max_batch) ? (n_frames - f0) : h->max_batch;
+        int rc = launch_presmooth(h, bgr_dev + (size_t)f0 * bgr_step * h->height, bgr_step, h->guide4, h->guide_pitch, n);
+        if (rc != KDME_OK) return rc;
+        rc = launch_filter(h, depth_dev + (size_t)f0 * plane, h->guide4, h->guide_pitch, out_dev + (size_t)f0 * plane, n,
+                           kStagePlain, nullptr, 0, 0);
+        if (rc != KDME_OK) return rc;
+    }
+    return KDME_OK;
+}
+
+extern "C" int jbf_process(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step) {
+    if (!h) return fail(KDME_EINVAL, "jbf_process: NULL handle");
+    return jbf_process_batch(h, depth_dev, bgr_dev, bgr_step, h->filtered_dev, 1);
+}
+
+extern "C" int jbf_upsample(jbf_handle* h, const float* depth_lo_dev, int wl, int hl, const uint8_t* bgr_hi_dev,
+                            size_t bgr_step, float* out_hi_dev) {
+    if (!h || !depth_lo_dev || !bgr_hi_dev || !out_hi_dev) return fail(KDME_EINVAL, "jbf_upsample: NULL argument");
+    if (wl <= 0 || hl <= 0 || wl > h->width || hl > h->height)
+        return fail(KDME_EINVAL, "jbf_upsample: low-res size must be positive and <= the handle's size");
+    DeviceGuard g(h->device);
+    int rc = launch_presmooth(h, bgr_hi_dev, bgr_step, h->guide4, h->guide_pitch, 1);
+    if (rc != KDME_OK) return rc;
+    return launch_filter(h, nullptr, h->guide4, h->guide_pitch, out_hi_dev, 1, kStageUpsample, depth_lo_dev, wl, hl);
+}
+
+static int ensure_pipe(jbf_handle* h, size_t bgr_step) {
+    if (h->s_h2d && h->pipe_bgr_step == bgr_step) return KDME_OK;
+    if (h->s_h2d && h->pipe_bgr_step != bgr_step) {
+        for (int b = 0; b < 2; b++) { cudaFree(h->pipe_bgr[b]); h->pipe_bgr[b] = nullptr; }
+    }
+    const size_t plane = (size_t)h->width * h->height;
+    if (!h->s_h2d) {
+        CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CK(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
+            CK(cudaMalloc(&h->pipe_depth[b], plane * h->max_batch * sizeof(float)));
+            CK(cudaMalloc(&h->pipe_out[b], plane * h->max_batch * sizeof(float)));
+        }
+    }
+    for (int b = 0; b < 2; b++) CK(cudaMalloc(&h->pipe_bgr[b], bgr_step * h->height * h->max_batch));
+    h->pipe_bgr_step = bgr_step;
+    return KDME_OK;
+}
+
+extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const uint8_t* bgr_host, size_t bgr_step,
+                                float* out_host, int n_frames) {
+    if (!h || !depth_host || !bgr_host || !out_host) return fail(KDME_EINVAL, "jbf_process_host: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_process_host: n_frames must be >= 1");
+    if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
+    if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
+    DeviceGuard g(h->device);
+    int rc = ensure_pipe(h, bgr_step);
+    if (rc != KDME_OK) return rc;
+    const size_t plane = (size_t)h->width * h->height;
+    const size_t bgr_frame = bgr_step * h->height;
+    // order the pipeline after work already queued on the handle's stream
+    int chunk = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch, ++chunk) {
+        const int n = (n_frames - f0 < h->max_batch) ? (n_frames - f0) : h->max_batch;
+        const int b = chunk & 1;
+        if (chunk >= 2) {
+            CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[b], 0));  // inputs of chunk-2 consumed
+        }
+        CK(cudaMemcpyAsync(h->pipe_depth[b], depth_host + (size_t)f0 * plane, plane * n * sizeof(float),
+                           cudaMemcpyHostToDevice, h->s_h2d));
+        CK(cudaMemcpyAsync(h->pipe_bgr[b], bgr_host + (size_t)f0 * bgr_frame, bgr_frame * n, cudaMemcpyHostToDevice,
+                           h->s_h2d));
+        CK(cudaEventRecord(h->ev_in[b], h->s_h2d));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        if (chunk >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));  // out[b] drained
+        rc = launch_presmooth(h, h->pipe_bgr[b], bgr_step, h->guide4, h->guide_pitch, n);
+        if (rc != KDME_OK) return rc;
+        rc = launch_filter(h, h->pipe_depth[b], h->guide4, h->guide_pitch, h->pipe_out[b], n, kStagePlain, nullptr, 0, 0);
+        if (rc != KDME_OK) return rc;
+        CK(cudaEventRecord(h->ev_done[b], h->stream));
+        CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[b], 0));
+        CK(cudaMemcpyAsync(out_host + (size_t)f0 * plane, h->pipe_out[b], plane * n * sizeof(float),
+                           cudaMemcpyDeviceToHost, h->s_d2h));
+        CK(cudaEventRecord(h->ev_free[b], h->s_d2h));
+    }
+    CK(cudaStreamSynchronize(h->s_d2h));
+    CK(cudaStreamSynchronize(h->stream));
+    return KDME_OK;
+}
+
+extern "C" float* jbf_filtered_device(jbf_handle* h) { return h ? h->filtered_dev : nullptr; }
+
+extern "C" const float* jbf_filtered_host(jbf_handle* h) {
+    if (!h) { fail(KDME_EINVAL, "jbf_filtered_host: NULL handle"); return nullptr; }
+    DeviceGuard g(h->device);
+    const size_t bytes = (size_t)h->width * h->height * sizeof(float);
+    if (!h->filtered_host && cudaMallocHost(&h->filtered_host, bytes) != cudaSuccess) {
+        fail(KDME_EINVAL, "jbf_filtered_host: cudaMallocHost failed");
+        return nullptr;
+    }
+    if (cudaMemcpyAsync(h->filtered_host, h->filtered_dev, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess) {
+        fail(KDME_EINVAL, "jbf_filtered_host: D2H copy failed");
+        return nullptr;
+    }
+    return h->filtered_host;
+}
+
+extern "C" const uint8_t* jbf_guide4_device(jbf_handle* h, size_t* step) {
+    if (!h) return nullptr;
+    if (step) *step = (size_t)h->guide_pitch * 4;
+    return reinterpret_cast<const uint8_t*>(h->guide4);
+}
+
+extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
+    if (!h) return nullptr;
+    DeviceGuard g(h->device);
+    if (!h->smooth_bgr && cudaMalloc(&h->smooth_bgr, (size_t)h->width * h->height * 3) != cudaSuccess) {
+        fail(KDME_EINVAL, "jbf_smooth_device: cudaMalloc failed");
+        return nullptr;
+    }
+    dim3 blk(128), grd((h->width + 127) / 128, h->height);
+    guide4_to_bgr_kernel<<<grd, blk, 0, h->stream>>>(h->guide4, h->guide_pitch, h->smooth_bgr, h->width, h->height);
+    if (step) *step = (size_t)h->width * 3;
+    return h->smooth_bgr;
+}
+
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x100)) : -1; }
+
+// ------------------------------------------------------------------ MRF (next row f1)
+extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,
+                       int window_radius, float color_sigma, float smooth_sigma) {
+    if (!h || !depth_dev || !bgr_dev || !out_dev) return fail(KDME_EINVAL, "jbf_mrf: NULL argument");
+    if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "jbf_mrf: bad radius");
+    if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
+    DeviceGuard g(h->device);
+    dim3 blk(128), grd((h->width + 127) / 128, h->height, 1);
+    bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr_dev, (long long)bgr_step, 0, h->guide4, h->guide_pitch, 0,
+                                                     h->width, h->height);
+    CK(cudaGetLastError());
+    constexpr int TW = 32, TH = 8;
+    const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
+    dim3 g2((h->width + TW - 1) / TW, (h->height + TH - 1) / TH);
+    mrf_kernel<TW, TH><<<g2, TW * TH, (size_t)SP * SH * 8, h->stream>>>(depth_dev, h->guide4, h->guide_pitch, out_dev,
+                                                                        h->width, h->height, window_radius,
+                                                                        color_sigma, smooth_sigma);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+extern "C" int kdme_projective_to_real(const float* depth_dev, float* xyz_dev, int width, int height, float fx,
+                                       float fy, int cx, int cy, void* stream) {
+    if (!depth_dev || !xyz_dev || width <= 0 || height <= 0) return fail(KDME_EINVAL, "projective_to_real: bad argument");
+    const long long n = (long long)width * height;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    projective_to_real_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(depth_dev, xyz_dev, width, height, fx, fy, cx, cy);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+// ------------------------------------------------------------------ guided fill
+extern "C" int kdme_guided_fill(const float* depth_dev, const int32_t* labels_dev, const uint8_t* bgr_dev,
+                                size_t bgr_step, float* out_dev, int width, int height, int window_radius,
+                                float sigma_spatial, float sigma_color, float sigma_depth, void* stream) {
+    if (!depth_dev || !bgr_dev || !out_dev) return fail(KDME_EINVAL, "kdme_guided_fill: NULL argument");
+    if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "kdme_guided_fill: bad size");
+    if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "kdme_guided_fill: bad radius");
+    if (depth_dev == out_dev) return fail(KDME_EINVAL, "kdme_guided_fill: in-place operation is not supported");
+    if (bgr_step == 0) bgr_step = (size_t)3 * width;
+    const int ws = 2 * window_radius + 1;
+    std::vector<float> lut;
+    host_spatial_lut(lut, ws, sigma_spatial);
+    GuidedParams p;
+    if (ws * ws > (int)(sizeof(p.spatial) / sizeof(float))) return fail(KDME_ENOTSUP, "kdme_guided_fill: window too large");
+    for (int i = 0; i < ws * ws; i++) p.spatial[i] = lut[i];
+    p.width = width; p.height = height; p.radius = window_radius;
+    p.depth = depth_dev; p.labels = labels_dev; p.bgr = bgr_dev; p.bgr_step = (long long)bgr_step; p.out = out_dev;
+    p.sigma_c = sigma_color; p.sigma_d = sigma_depth;
+    constexpr int TW = 32, TH = 8;
+    const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
+    dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
+    guided_fill_kernel<TW, TH><<<grd, TW * TH, (size_t)SP * SH * 12, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+// ------------------------------------------------------------------ Buffer2D
+struct buf2d_handle {
+    int width = 0, height = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    float* dw = nullptr;        // weighted_d[width*height]
+    float* scratch = nullptr;   // lazily allocated (u16 host path)
+    uint16_t* scratch16 = nullptr;
+};
+
+static int buf_blocks(long long n) {
+    long long b = ((n >> 2) + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148LL * 8) b = 148LL * 8;  // grid-stride; 8 CTAs of 256 threads per SM
+    return (int)b;
+}
+
+template <int OP>
+static int buf_launch(buf2d_handle* b, const float* data, float* out, int n_frames) {
+    DeviceGuard g(b->device);
+    const long long n = (long long)b->width * b->height;
+    buf2d_kernel<OP><<<buf_blocks(n), 256, 0, b->stream>>>(b->dw, data, out, n, b->width, n_frames);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
+extern "C" int buf2d_create(buf2d_handle** out, int width, int height, int device, void* stream) {
+    if (!out) return fail(KDME_EINVAL, "buf2d_create: out is NULL");
+    *out = nullptr;
+    if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "buf2d_create: width/height must be positive");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(KDME_EINVAL, "buf2d_create: no such CUDA device");
+    DeviceGuard g(device);
+    buf2d_handle* b = new buf2d_handle();
+    b->width = width; b->height = height; b->device = device; b->stream = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&b->dw, (size_t)width * height * 2 * sizeof(float));
+    if (e != cudaSuccess) { delete b; return fail(-(int)e, "buf2d_create: cudaMalloc failed"); }
+    int rc = buf_launch<kBufInit>(b, nullptr, nullptr, 0);
+    if (rc != KDME_OK) { cudaFree(b->dw); delete b; return rc; }
+    *out = b;
+    return KDME_OK;
+}
+extern "C" void buf2d_destroy(buf2d_handle* b) {
+    if (!b) return;
+    DeviceGuard g(b->device);
+    cudaFree(b->dw); cudaFree(b->scratch); cudaFree(b->scratch16);
+    delete b;
+}
+extern "C" int buf2d_init(buf2d_handle* b) {
+    if (!b) return fail(KDME_EINVAL, "buf2d_init: NULL handle");
+    return buf_launch<kBufInit>(b, nullptr, nullptr, 0);
+}
+extern "C" int buf2d_insert_f32(buf2d_handle* b, const float* data_dev) {
+    if (!b || !data_dev) return fail(KDME_EINVAL, "buf2d_insert_f32: NULL argument");
+    if (reinterpret_cast<uintptr_t>(data_dev) & 15) return fail(KDME_EINVAL, "buf2d_insert_f32: data must be 16-byte aligned");
+    return buf_launch<kBufInsertF32>(b, data_dev, nullptr, 0);
+}
+extern "C" int buf2d_insert_dw(buf2d_handle* b, const float* dw_dev) {
+    if (!b || !dw_dev) return fail(KDME_EINVAL, "buf2d_insert_dw: NULL argument");
+    DeviceGuard g(b->device);
+    CK(cudaMemcpyAsync(b->dw, dw_dev, (size_t)b->width * b->height * 2 * sizeof(float), cudaMemcpyDeviceToDevice, b->stream));
+    return KDME_OK;
+}
+extern "C" int buf2d_insert_f32x2(buf2d_handle* b, const float* xy_dev) {
+    if (!b || !xy_dev) return fail(KDME_EINVAL, "buf2d_insert_f32x2: NULL argument");
+    if (reinterpret_cast<uintptr_t>(xy_dev) & 15) return fail(KDME_EINVAL, "buf2d_insert_f32x2: data must be 16-byte aligned");
+    return buf_launch<kBufInsertXY>(b, xy_dev, nullptr, 0);
+}
+extern "C" int buf2d_update_batch_f32(buf2d_handle* b, const float* data_dev, int n_frames) {
+    if (!b || !data_dev) return fail(KDME_EINVAL, "buf2d_update: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "buf2d_update: n_frames must be >= 1");
+    if (reinterpret_cast<uintptr_t>(data_dev) & 15) return fail(KDME_EINVAL, "buf2d_update: data must be 16-byte aligned");
+    if (n_frames > 1 && (((long long)b->width * b->height) & 3))
+        return fail(KDME_EINVAL, "buf2d_update_batch: width*height must be a multiple of 4 for batches");
+    return buf_launch<kBufUpdate>(b, data_dev, nullptr, n_frames);
+}
+extern "C" int buf2d_update_f32(buf2d_handle* b, const float* data_dev) { return buf2d_update_batch_f32(b, data_dev, 1); }
+extern "C" int buf2d_update_u16_host(buf2d_handle* b, const uint16_t* depth_host) {
+    if (!b || !depth_host) return fail(KDME_EINVAL, "buf2d_update_u16_host: NULL argument");
+    DeviceGuard g(b->device);
+    const long long n = (long long)b->width * b->height;
+    if (!b->scratch) CK(cudaMalloc(&b->scratch, n * sizeof(float)));
+    if (!b->scratch16) CK(cudaMalloc(&b->scratch16, n * sizeof(uint16_t)));
+    CK(cudaMemcpyAsync(b->scratch16, depth_host, n * sizeof(uint16_t), cudaMemcpyHostToDevice, b->stream));
+    u16_to_f32_kernel<<<buf_blocks(n * 4), 256, 0, b->stream>>>(b->scratch16, b->scratch, n);
+    CK(cudaGetLastError());
+    int rc = buf_launch<kBufUpdate>(b, b->scratch, nullptr, 1);
+    if (rc != KDME_OK) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return KDME_OK;
+}
+extern "C" int buf2d_get_depth(buf2d_handle* b, float* out_dev) {
+    if (!b || !out_dev) return fail(KDME_EINVAL, "buf2d_get_depth: NULL argument");
+    if (reinterpret_cast<uintptr_t>(out_dev) & 15) return fail(KDME_EINVAL, "buf2d_get_depth: out must be 16-byte aligned");
+    return buf_launch<kBufGetDepth>(b, nullptr, out_dev, 0);
+}
+extern "C" int buf2d_get_weight(buf2d_handle* b, float* out_dev) {
+    if (!b || !out_dev) return fail(KDME_EINVAL, "buf2d_get_weight: NULL argument");
+    if (reinterpret_cast<uintptr_t>(out_dev) & 15) return fail(KDME_EINVAL, "buf2d_get_weight: out must be 16-byte aligned");
+    return buf_launch<kBufGetWeight>(b, nullptr, out_dev, 0);
+}
+extern "C" float* buf2d_raw(buf2d_handle* b) { return b ? b->dw : nullptr; }

@@ -1,0 +1,116 @@
+// presmooth_kernels.cuh -- colour bilateral pre-smooth of the guide image.
+//
+// Stands in for the third-party call cv::gpu::bilateralFilter(color, smooth, 5,
+// 30.0f, 30.0f) at JointBilateralFilter/JointBilateralFilter.cu:285 (OpenCV 2.4.3
+// gpu module, not vendored in the reference): circular window dx^2+dy^2 <= r^2,
+// weight = exp(-space2/(2 ss^2)) * exp(-L1(dBGR)^2/(2 sc^2)), reflect-101 border,
+// round-to-nearest-even saturation to u8.
+//
+// Both exponentials come from LUTs built on the host (space: ksize^2 entries,
+// colour: 766 entries indexed by the integer L1 distance), multiplied in fp32 and
+// accumulated un-fused in tap order (dy outer, dx inner), so the result is
+// bit-identical to oracle/kdme_oracle.c:orc_presmooth_bgr given the same LUTs.
+//
+// Input: packed BGR u8x3 rows (cv::gpu::GpuMat CV_8UC3).  Output: the internal
+// u8x4 {B,G,R,0} guide (16-byte alignable rows, one 32-bit word per pixel) that the
+// JBF kernel stages with TMA.
+#pragma once
+#include "common.cuh"
+
+namespace kdme {
+
+constexpr int kPsMaxK = 9;  // largest supported pre-smooth kernel size
+
+struct PresmoothParams {
+    int width, height, n_frames;
+    const uint8_t* bgr;          // [n][H][bgr_step]
+    long long bgr_step;          // bytes per row
+    long long bgr_frame_stride;  // bytes
+    uint32_t* guide4;            // [n][H][guide_pitch]
+    int guide_pitch;             // words
+    long long guide_frame_stride;  // words
+    int ksize;
+    const float* space_lut;  // [ksize*ksize], < 0 outside the circle
+    const float* color_lut;  // [766]
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParams p) {
+    constexpr int NT = TW * TH;
+    constexpr int RMAX = kPsMaxK / 2;
+    constexpr int SPM = TW + 2 * RMAX, SHM = TH + 2 * RMAX;
+    __shared__ uint32_t sPix[SPM * SHM];
+    __shared__ float sCol[768];
+    __shared__ float sSp[kPsMaxK * kPsMaxK];
+    const int r = p.ksize / 2;
+    const int SP = TW + 2 * r, SH = TH + 2 * r;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
+
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = reflect101(x0 - r + sx, p.width), gy = reflect101(y0 - r + sy, p.height);
+        const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
+        sPix[idx] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+    }
+    for (int idx = tid; idx < 766; idx += NT) sCol[idx] = __ldg(p.color_lut + idx);
+    for (int idx = tid; idx < p.ksize * p.ksize; idx += NT) sSp[idx] = __ldg(p.space_lut + idx);
+    __syncthreads();
+
+    const int lx = tid % TW, ly = tid / TW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= p.width || gy >= p.height) return;
+    const uint32_t c = sPix[(ly + r) * SP + lx + r];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, ws = 0.f;
+    for (int dy = 0; dy < p.ksize; ++dy) {
+        for (int dx = 0; dx < p.ksize; ++dx) {
+            const float sw = sSp[dy * p.ksize + dx];
+            if (sw < 0.f) continue;
+            const uint32_t q = sPix[(ly + dy) * SP + lx + dx];
+            const uint32_t ad = __vabsdiffu4(q, c);
+            const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
+            const float w = __fmul_rn(sw, sCol[l1]);
+            s0 = __fadd_rn(s0, __fmul_rn(w, (float)(q & 0xffu)));
+            s1 = __fadd_rn(s1, __fmul_rn(w, (float)((q >> 8) & 0xffu)));
+            s2 = __fadd_rn(s2, __fmul_rn(w, (float)((q >> 16) & 0xffu)));
+            ws = __fadd_rn(ws, w);
+        }
+    }
+    const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0, ws)), 0.f), 255.f);
+    const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1, ws)), 0.f), 255.f);
+    const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2, ws)), 0.f), 255.f);
+    const uint32_t o = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
+    p.guide4[(long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx] = o;
+}
+
+// packed BGR -> internal u8x4 without smoothing (pre-smooth disabled, guided fill, MRF)
+__global__ void bgr_to_guide4_kernel(const uint8_t* bgr, long long bgr_step, long long bgr_frame_stride,
+                                     uint32_t* guide4, int guide_pitch, long long guide_frame_stride, int width,
+                                     int height) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
+    const int frame = blockIdx.z;
+    if (gx >= width || gy >= height) return;
+    const uint8_t* q = bgr + (long long)frame * bgr_frame_stride + (long long)gy * bgr_step + 3 * gx;
+    guide4[(long long)frame * guide_frame_stride + (long long)gy * guide_pitch + gx] =
+        (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+}
+
+// internal u8x4 -> packed BGR (getSmoothImage_Device, JointBilateralFilter.cpp:47-49)
+__global__ void guide4_to_bgr_kernel(const uint32_t* guide4, int guide_pitch, uint8_t* bgr, int width, int height) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
+    if (gx >= width || gy >= height) return;
+    const uint32_t v = guide4[(long long)gy * guide_pitch + gx];
+    uint8_t* q = bgr + ((long long)gy * width + gx) * 3;
+    q[0] = (uint8_t)(v & 0xff);
+    q[1] = (uint8_t)((v >> 8) & 0xff);
+    q[2] = (uint8_t)((v >> 16) & 0xff);
+}
+
+}  // namespace kdme
