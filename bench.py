@@ -1,0 +1,317 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native joint-bilateral depth-enhancement path.
+
+Metric (BASELINE.json): JBF Mpixel/s at 640x480, r=7 (window 15), reference sigmas 70/50/20 and
+guide pre-smooth (5, 30, 30), on a synthetic Kinect-v1 RGB-D stream (configs[1]).  One "step" is
+one pass of JointBilateralFilter::Process over a stream of --frames frames per GPU (frame-sharded,
+no data-path collective => weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this framework
+    python bench.py --impl reference [...]                       # the reference's own CPU path
+
+For N > 1 launch one rank per GPU with torchrun (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from env).
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, RADIUS = 640, 480, 7
+SIGMAS = (70.0, 50.0, 20.0)
+# 33 flop + 3 exp per tap per pixel (reference kernel text), + 4 flop/pixel epilogue
+FLOP_PER_PIXEL = 33 * (2 * RADIUS + 1) ** 2 + 4
+BYTES_PER_PIXEL = 11  # depth f32 in + BGR u8x3 in + filtered f32 out
+FP32_NOMINAL_TFLOPS = 74.4  # 148 SM x 128 FMA/clk x 2 x 1.965 GHz
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step (configs[1]: 4096)")
+    ap.add_argument("--chunk", type=int, default=64, help="frames per launch pair (handle max_batch)")
+    ap.add_argument("--e2e-frames", type=int, default=512, help="frames per e2e step (host buffers)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(s for s, pw in zip(sm, power) if pw >= 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def fp32_peak():
+    """FFMA peak measured live on this GPU by tools/pipe_microbench; nominal otherwise."""
+    exe = os.path.join(ROOT, "tools", "pipe_microbench")
+    if os.path.isfile(exe):
+        try:
+            res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+            micro = json.loads(res.stdout.strip().splitlines()[-1])
+            return micro["ffma_tflops"], "measured (tools/pipe_microbench FFMA, this run)", micro
+        except Exception:
+            pass
+    return FP32_NOMINAL_TFLOPS, "nominal (148 SM x 128 FMA/clk x 2 x 1.965 GHz)", None
+
+
+def cpu_baseline(budget_s: float, frames_np=None):
+    """The reference's own kernel text on the host cores (oracle/_ref), else the C restatement (port)."""
+    import numpy as np
+    import oracle
+    from kinectdepthmapenhancement_b200 import synth
+    oracle.build()
+    kind = "reference" if oracle.ref_available() else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    cores = oracle.n_cores()
+    d, c = synth.rgbd_frame(W, H, 1234, 0)
+    d, c = d.numpy(), c.numpy()
+    t0 = time.perf_counter()
+    g = oracle.presmooth(c)
+    oracle.jbf(d, g, 2 * RADIUS + 1, *SIGMAS, precision="f32", impl=impl, threads=cores)
+    t1 = time.perf_counter() - t0
+    n = max(1, min(64, int(budget_s / max(t1, 1e-3)) - 1))
+    t0 = time.perf_counter()
+    for i in range(n):
+        g = oracle.presmooth(c)
+        oracle.jbf(d, g, 2 * RADIUS + 1, *SIGMAS, precision="f32", impl=impl, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n * W * H / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+            "sample": f"{n} frame(s) of the same 640x480 r=7 stream (pre-smooth + two-pass filter), "
+                      f"{'reference kernel text (oracle/_ref)' if kind == 'reference' else 'C restatement (oracle/)'}"
+                      f", OpenMP over rows, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle
+    from kinectdepthmapenhancement_b200 import synth
+    oracle.build()
+    kind = "reference" if oracle.ref_available() else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    cores = oracle.n_cores()
+    d, c = synth.rgbd_frame(W, H, 1234, 0)
+    d, c = d.numpy(), c.numpy()
+
+    def one_frame():
+        g = oracle.presmooth(c)
+        oracle.jbf(d, g, 2 * RADIUS + 1, *SIGMAS, precision="f32", impl=impl, threads=cores)
+
+    t0 = time.perf_counter(); one_frame(); t1 = time.perf_counter() - t0
+    total_steps = args.steps + args.warmup
+    per_step = max(1, min(16, int(120.0 / total_steps / max(t1, 1e-3))))
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            one_frame()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            one_frame()
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step * W * H / dt / 1e6
+    sample = f"{per_step} frame(s) per step of the 640x480 r=7 stream, {kind}, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "JBF Mpixel/s at 640x480 r=7", "value": v, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic Kinect-v1 640x480 RGB-D stream, r=7, reference sigmas 70/50/20, "
+                               "pre-smooth (5,30,30); bounded sample per step", "frames_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------ this framework
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from kinectdepthmapenhancement_b200 import JointBilateralFilter, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_frames = args.frames
+    first = rank * n_frames  # frame-sharded: rank g owns frames [g*F, (g+1)*F)
+    # 64 distinct synthetic frames tiled over the shard: every frame is an independent full-size unit,
+    # 4096 frames = 8.8 GB of inputs per GPU (>> 126 MB L2), so no L2 flush is needed between steps.
+    depth, bgr = synth.rgbd_stream(n_frames, W, H, seed=1234, first_frame=first, device=dev, distinct=64)
+    out = torch.empty_like(depth)
+    jbf = JointBilateralFilter(W, H, *SIGMAS, window_radius=RADIUS, max_batch=args.chunk, device=local)
+    launches_per_step = 2 * ((n_frames + args.chunk - 1) // args.chunk)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        jbf.process_batch(depth, bgr, out)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        jbf.process_batch(depth, bgr, out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # dominant kernel alone: the two-pass filter on the already smoothed guide, same data, same stream
+    guide4 = jbf.presmooth(bgr[:args.chunk])
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_k = 0
+    k0.record()
+    for _ in range(max(1, args.steps)):
+        for f0 in range(0, n_frames - args.chunk + 1, args.chunk):
+            jbf.filter_guide4(depth[f0:f0 + args.chunk], guide4, out[f0:f0 + args.chunk])
+            n_k += 1
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / n_k
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_pixels = world * n_frames * W * H * args.steps
+    value = total_pixels / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_frames, n_frames)
+        dh = depth[:ne].cpu().pin_memory()
+        ch = bgr[:ne].cpu().pin_memory()
+        oh = torch.empty_like(dh).pin_memory()
+        jbf.process_host(dh, ch, oh)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(2, args.steps)
+        for _ in range(e_steps):
+            jbf.process_host(dh, ch, oh)   # synchronous: returns when oh is complete
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ne * W * H * e_steps / float(te.item()) / 1e6, "unit": "Mpixel/s",
+               "h2d_bytes_per_step": ne * W * H * 7, "d2h_bytes_per_step": ne * W * H * 4,
+               "frames_per_step": ne, "steps": e_steps,
+               "how": "jbf_process_host: pinned host depth+BGR -> H2D -> pre-smooth + filter -> D2H, "
+                      "double-buffered chunks; host wall clock, max over ranks"}
+        if not torch.equal(oh[: args.chunk], out[: args.chunk].cpu()):
+            e2e["warning"] = "e2e output differs from device path"
+
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        fp32_tf, fp32_src, micro = fp32_peak()
+        px_per_launch = args.chunk * W * H
+        ach_tf = px_per_launch * FLOP_PER_PIXEL / (kern_ms * 1e-3) / 1e12
+        ach_gbs = px_per_launch * BYTES_PER_PIXEL / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "JBF Mpixel/s at 640x480 r=7", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: synthetic Kinect-v1 640x480 RGB-D stream, r=7 (window 15), sigmas "
+                                   "70/50/20, guide pre-smooth (5,30,30), frame-sharded",
+                       "frames_per_gpu": n_frames, "frames_per_launch": args.chunk, "parallelism": f"frames x{world}",
+                       "l2": "inputs (8.8 GB/GPU) larger than L2; no flush needed"},
+            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "roofline": {
+                "kernel": "jbf_fast_kernel<7,64,16> (two-pass filter; presmooth_kernel is the other launch)",
+                "bound": "fp32", "achieved": ach_tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": ach_tf / fp32_tf,
+                "peak_source": fp32_src, "flop_per_pixel": FLOP_PER_PIXEL, "pixels_per_launch": px_per_launch,
+                "kernel_ms_per_launch": kern_ms, "kernel_mpixel_s": px_per_launch / (kern_ms * 1e-3) / 1e6,
+                "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
+                        "peak_source": peaks_kind + " (MEASURED_PEAKS.json)", "bytes_per_pixel": BYTES_PER_PIXEL},
+                "traffic": None,
+                "note": "the path is FP32/MUFU-issue bound (intensity 675 flop/B vs balance ~11), see DESIGN.md",
+            },
+            "microbench": micro,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

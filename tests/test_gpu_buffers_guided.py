@@ -1,0 +1,103 @@
+"""GPU parity: Buffer2D (bit-exact: un-fused fp32 with integer gate) and the guided fill."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import synth_np
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (70, 50), (33, 17), (1, 1), (512, 424)])
+def test_buffer2d_bit_exact(w, h):
+    from kinectdepthmapenhancement_b200 import Buffer2D
+    depth, _ = synth_np(w, h, seed=31, frame=0)
+    rng = np.random.default_rng(w)
+    frames = np.stack([np.where(depth > 50, depth + rng.uniform(-15, 15, depth.shape), depth)
+                       for _ in range(9)]).astype(np.float32)
+    frames[2, : h // 2] = 0
+    frames[5] = frames[5] * 1.3
+    b = Buffer2D(w, h)
+    o = oracle.Buffer2D(w, h)
+    assert torch.count_nonzero(b.getRawPointer()) == 0
+    for f in frames:
+        b.updateData(torch.from_numpy(f).cuda())
+        o.update(f)
+    assert np.array_equal(b.getDepthMap().cpu().numpy().view(np.uint32), o.depth_map().view(np.uint32))
+    assert np.array_equal(b.getWeightMap().cpu().numpy(), o.weight_map())
+    assert np.array_equal(b.getRawPointer().cpu().numpy().view(np.uint32), o.raw().view(np.uint32))
+    # fused multi-frame update == frame by frame
+    if (w * h) % 4 == 0:
+        b2 = Buffer2D(w, h)
+        b2.updateData(torch.from_numpy(frames).cuda())
+        assert torch.equal(b2.getRawPointer(), b.getRawPointer())
+    # insertData(float*), insertData(float2*) (w = row index quirk), insertData(weighted_d*)
+    b.insertData(torch.from_numpy(frames[0]).cuda())
+    o.insert(frames[0])
+    assert np.array_equal(b.getRawPointer().cpu().numpy(), o.raw())
+    xy = np.stack([frames[1], frames[2]], axis=-1).astype(np.float32)
+    b.insertData2(torch.from_numpy(xy).cuda())
+    o.insert_f32x2(xy)
+    assert np.array_equal(b.getRawPointer().cpu().numpy(), o.raw())
+    b3 = Buffer2D(w, h)
+    b3.insertWeighted(b.getRawPointer().clone())
+    assert torch.equal(b3.getRawPointer(), b.getRawPointer())
+    b.initDeviceMemoryElements()
+    assert torch.count_nonzero(b.getRawPointer()) == 0
+
+
+def test_buffer2d_u16_host_path_and_golden(golden_dir):
+    from kinectdepthmapenhancement_b200 import Buffer2D
+    gold = np.load(os.path.join(golden_dir, "ref_golden.npz"))
+    b = Buffer2D(96, 64)
+    for f in gold["buf_frames"]:
+        b.updateData(torch.from_numpy(f).cuda())
+    assert np.array_equal(b.getDepthMap().cpu().numpy().view(np.uint32), gold["buf_depth"].view(np.uint32))
+    assert np.array_equal(b.getWeightMap().cpu().numpy(), gold["buf_weight"])
+    d16 = np.clip(gold["depth"], 0, 65535).astype(np.uint16)
+    b = Buffer2D(96, 64)
+    b.updateDataU16Host(torch.from_numpy(d16.view(np.int16)))
+    o = oracle.Buffer2D(96, 64)
+    o.update(d16.astype(np.float32))
+    assert np.array_equal(b.getRawPointer().cpu().numpy(), o.raw())
+
+
+@pytest.mark.parametrize("w,h,radius,use_labels", [(160, 120, 3, True), (160, 120, 3, False), (70, 50, 5, True)])
+def test_guided_fill_vs_oracle(w, h, radius, use_labels):
+    from kinectdepthmapenhancement_b200 import guided_fill
+    depth, bgr = synth_np(w, h, seed=17, frame=radius)
+    labels = ((np.arange(h)[:, None] // 16) * 64 + (np.arange(w)[None, :] // 12)).astype(np.int32) if use_labels else None
+    want = oracle.guided_fill(depth, bgr, labels, 2 * radius + 1)
+    got = guided_fill(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(),
+                      torch.from_numpy(labels).cuda() if use_labels else None, radius).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok] > 0, want[ok] > 0)
+    err = np.abs(got[ok].astype(np.float64) - want[ok])
+    # the oracle here is the reference's own fp32 evaluation (its round-off included)
+    assert np.quantile(err, 0.99) <= 5e-3 and np.median(err) <= 5e-4
+    print(f"\nguided fill {w}x{h} r={radius}: median {np.median(err):.2e} p99 {np.quantile(err, 0.99):.2e} max {err.max():.2e}")
+
+
+def test_guided_fill_golden(golden_dir):
+    from kinectdepthmapenhancement_b200 import guided_fill
+    gold = np.load(os.path.join(golden_dir, "ref_golden.npz"))
+    got = guided_fill(torch.from_numpy(gold["depth"]).cuda(), torch.from_numpy(gold["bgr"]).cuda(),
+                      torch.from_numpy(gold["labels"]).cuda(), 3).cpu().numpy()
+    want = gold["guided_ws7"]
+    assert np.array_equal(got > 0, want > 0)
+    assert np.quantile(np.abs(got - want), 0.99) <= 5e-3
+
+
+def test_jbf_golden(golden_dir):
+    """GPU vs the reference kernel text's own outputs (fp32): agreement to the reference's round-off."""
+    from test_gpu_jbf import gpu_filter
+    gold = np.load(os.path.join(golden_dir, "ref_golden.npz"))
+    for key, r in (("jbf_ws5", 2), ("jbf_ws15", 7)):
+        out, _ = gpu_filter(gold["depth"], gold["guide"], r)
+        assert np.array_equal(out > 0, gold[key] > 0)
+        assert np.median(np.abs(out - gold[key])) <= 1e-3
