@@ -24,7 +24,7 @@
  * this path.  The restatement is pinned instead against
  * the reference's own kernel text compiled for the host (oracle/_ref, built by
  * oracle/build_ref.py from the sources where they lie under /root/reference):
- * tests/test_oracle_vs_ref.py asserts bit-for-bit equality in fp32 whenever
+ * tests/test_oracle.py asserts bit-for-bit equality in fp32 whenever
  * oracle/_ref is populated.  The third-party guide pre-smooth
  * (cv::gpu::bilateralFilter, OpenCV 2.4.3, not under /root/reference) is
  * "parity unpinned": restated from its published algorithm and cross-checked
@@ -368,6 +368,91 @@ ORC_API void orc_guided_fill_f32(int width, int height, const float *depth, cons
             } else {
                 out[y * width + x] = 0.0f;
             }
+        }
+    }
+}
+
+/* fp64 evaluation of the same three sweeps ("exact-math" oracle for the guided fill).  Sums,
+ * mean and deviation are in double; the colour-sigma recurrence stays the reference's fp32
+ * sequence (it is a discrete state machine: sigma *= 0.3f or sigma = adaptive, :172-175) driven
+ * by the fp32 rounding of 5.0*deviation/mean^2; the skip-if-zero guards are the explicit
+ * arg < -150 ln2 tests; -0/0 (sigma^2 underflowed to 0 with cd == 0) poisons the pixel with NaN
+ * exactly as expf(NaN) does in the reference. */
+ORC_API void orc_guided_fill_f64(int width, int height, const float *depth, const uint8_t *guide,
+                                 const int32_t *labels, const float *spatial, float *out,
+                                 double *mean_out /*nullable*/, int window_size, float color_sigma_in,
+                                 float depth_sigma, int n_threads)
+{
+    int half = window_size / 2;
+    double kd = (depth_sigma != 0.0f) ? 1.0 / (2.0 * (double)depth_sigma * (double)depth_sigma) : 0.0;
+    (void)n_threads;
+#pragma omp parallel for schedule(dynamic, 2) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int y = 0; y < height; y++) {
+        for (int x = 0; x < width; x++) {
+            int lp = labels ? labels[y * width + x] : 0;
+            const uint8_t *gp = guide + (size_t)(y * width + x) * 3;
+            double a = 0.0, wt = 0.0;
+            double den0 = 2.0 * (double)color_sigma_in * (double)color_sigma_in;
+            for (int i = -half; i <= half; i++)
+                for (int j = -half; j <= half; j++) {
+                    int xj = x + j, yi = y + i;
+                    if (!(xj >= 0 && xj < width && yi >= 0 && yi < height)) continue;
+                    if (!(depth[yi * width + xj] > 50.0f)) continue;
+                    if (lp != (labels ? labels[yi * width + xj] : 0)) continue;
+                    const uint8_t *gq = guide + (size_t)(yi * width + xj) * 3;
+                    double c0 = (double)gp[0] - gq[0], c1 = (double)gp[1] - gq[1], c2 = (double)gp[2] - gq[2];
+                    double cd = c0 * c0 + c1 * c1 + c2 * c2;
+                    double f = 1.0;
+                    float s = spatial[(i + half) * window_size + (j + half)];
+                    if (s != 0.0f) f *= (double)s;
+                    if (color_sigma_in != 0.0f && cd / den0 <= ORC_EXP_ZERO_ARG) f *= exp(-cd / den0);
+                    a += (double)depth[yi * width + xj] * f;
+                    wt += f;
+                }
+            if (mean_out) mean_out[y * width + x] = 0.0;
+            if (!(wt > 0.0)) { out[y * width + x] = 0.0f; continue; }
+            double m = a / wt;
+            if (mean_out) mean_out[y * width + x] = m;
+            double dev = 0.0; int count = 0;
+            for (int i = -half; i <= half; i++)
+                for (int j = -half; j <= half; j++) {
+                    int xj = x + j, yi = y + i;
+                    if (!(xj >= 0 && xj < width && yi >= 0 && yi < height)) continue;
+                    if (!(depth[yi * width + xj] > 50.0f)) continue;
+                    if (lp != (labels ? labels[yi * width + xj] : 0)) continue;
+                    dev += fabs((double)depth[yi * width + xj] - m);
+                    count++;
+                }
+            if (count != 0) dev /= (double)count;
+            float mf = (float)m;
+            float adaptive = (float)(5.0 * dev / (double)(mf * mf));
+            float sigma = color_sigma_in;
+            double num = 0.0, den = 0.0;
+            int poisoned = 0;
+            for (int i = -half; i <= half; i++)
+                for (int j = -half; j <= half; j++) {
+                    int xj = x + j, yi = y + i;
+                    if (!(xj >= 0 && xj < width && yi >= 0 && yi < height)) continue;
+                    if (!(depth[yi * width + xj] > 50.0f)) continue;
+                    const uint8_t *gq = guide + (size_t)(yi * width + xj) * 3;
+                    double c0 = (double)gp[0] - gq[0], c1 = (double)gp[1] - gq[1], c2 = (double)gp[2] - gq[2];
+                    double cd = c0 * c0 + c1 * c1 + c2 * c2;
+                    double f = 1.0;
+                    float s = spatial[(i + half) * window_size + (j + half)];
+                    if (s != 0.0f) f *= (double)s;
+                    if (sigma != 0.0f) {
+                        if (adaptive > sigma * 0.3f) sigma = adaptive; else sigma *= 0.3f;
+                        float dn = 2 * (sigma * sigma);   /* fp32: may underflow to 0 */
+                        if (dn == 0.0f) { if (cd == 0.0) poisoned = 1; /* cd > 0: expf(-inf) = 0, skipped */ }
+                        else if (cd / (double)dn <= ORC_EXP_ZERO_ARG) f *= exp(-cd / (double)dn);
+                    }
+                    double e = (double)depth[yi * width + xj] - m;
+                    if (depth_sigma != 0.0f && e * e * kd <= ORC_EXP_ZERO_ARG) f *= exp(-e * e * kd);
+                    num += (double)depth[yi * width + xj] * f;
+                    den += f;
+                }
+            if (poisoned) out[y * width + x] = NAN;
+            else out[y * width + x] = (den == 0.0) ? 0.0f : (float)(num / den);
         }
     }
 }

@@ -71,16 +71,22 @@ def test_guided_fill_vs_oracle(w, h, radius, use_labels):
     from kinectdepthmapenhancement_b200 import guided_fill
     depth, bgr = synth_np(w, h, seed=17, frame=radius)
     labels = ((np.arange(h)[:, None] // 16) * 64 + (np.arange(w)[None, :] // 12)).astype(np.int32) if use_labels else None
-    want = oracle.guided_fill(depth, bgr, labels, 2 * radius + 1)
+    ws = 2 * radius + 1
+    o32 = oracle.guided_fill(depth, bgr, labels, ws)
+    o64 = oracle.guided_fill(depth, bgr, labels, ws, precision="f64")
     got = guided_fill(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(),
                       torch.from_numpy(labels).cuda() if use_labels else None, radius).cpu().numpy()
-    assert np.array_equal(np.isnan(got), np.isnan(want))
-    ok = ~np.isnan(want)
-    assert np.array_equal(got[ok] > 0, want[ok] > 0)
-    err = np.abs(got[ok].astype(np.float64) - want[ok])
-    # the oracle here is the reference's own fp32 evaluation (its round-off included)
-    assert np.quantile(err, 0.99) <= 5e-3 and np.median(err) <= 5e-4
-    print(f"\nguided fill {w}x{h} r={radius}: median {np.median(err):.2e} p99 {np.quantile(err, 0.99):.2e} max {err.max():.2e}")
+    assert np.array_equal(np.isnan(got), np.isnan(o64))
+    ok = ~np.isnan(o64)
+    assert np.array_equal(got[ok] > 0, o64[ok] > 0), "valid/hole mask differs"
+    err = np.abs(got[ok].astype(np.float64) - o64[ok])
+    e32 = np.abs(o32[ok].astype(np.float64) - o64[ok])
+    print(f"\nguided fill {w}x{h} r={radius}: gpu vs f64 median {np.median(err):.2e} p99 {np.quantile(err, 0.99):.2e} "
+          f"max {err.max():.2e} | reference-order fp32 vs f64 p99 {np.quantile(e32, 0.99):.2e} max {e32.max():.2e}")
+    # float tolerance: 1e-3 mm on the bulk; never worse than the reference's own fp32 arithmetic
+    assert np.median(err) <= 2.5e-4
+    assert np.quantile(err, 0.99) <= max(1e-3, np.quantile(e32, 0.99))
+    assert err.max() <= max(0.05, e32.max())
 
 
 def test_guided_fill_golden(golden_dir):

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) pipe_kernel(float* out, float a, float b,
                 if (OP == 3) asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(u[i]) : "r"(ua), "r"(0));
                 if (OP == 4) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(ua), "r"(u[(i + 1) % NCH]));
                 if (OP == 5) {  // pass-1 tap body: VABSDIFF4, IDP.4A, FADD, FFMA, MUFU.EX2, FFMA, FADD
-                    uint32_t ad = __vabsdiffu4(u[i], ua + it);
+                    uint32_t ad = __vabsdiffu4(u[i], ua + it * 4 + rep);
                     float cdf = __uint_as_float(__dp4a(ad, ad, 0x4B000000u)) - 8388608.0f;
                     float f;
                     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(fmaf(cdf, a, b)));
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) pipe_kernel(float* out, float a, float b,
                     x[(i + 1) % NCH] += f;
                 }
                 if (OP == 6) {  // pass-2 tap body: + FADD, FSETP, predicated FFMA
-                    uint32_t ad = __vabsdiffu4(u[i], ua + it);
+                    uint32_t ad = __vabsdiffu4(u[i], ua + it * 4 + rep);
                     float cdf = __uint_as_float(__dp4a(ad, ad, 0x4B000000u)) - 8388608.0f;
                     float arg = fmaf(cdf, a, b);
                     float e = x[(i + 2) % NCH] - b;
