@@ -170,10 +170,19 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         const uint4 m4 = *reinterpret_cast<const uint4*>(sM + c);
         gp[0] = g4.x; gp[1] = g4.y; gp[2] = g4.z; gp[3] = g4.w;
         // per-thread accumulation origin: first valid own pixel (scaled, tile-relative)
+        bool has = true;
         d0 = (m4.x == kMagicValid) ? d4.x
            : (m4.y == kMagicValid) ? d4.y
            : (m4.z == kMagicValid) ? d4.z
-           : (m4.w == kMagicValid) ? d4.w : 0.f;
+           : (m4.w == kMagicValid) ? d4.w : (has = false, 0.f);
+        // no valid own pixel (hole filling): borrow the origin of the nearest thread of the same
+        // tile row that has one (xor distances 1,2,4,8 within the TW/4 = 16 lanes of the row)
+#pragma unroll
+        for (int o = 1; o < TW / 4 && o < 32; o <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, d0, o);
+            const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, o) != 0;
+            if (!has && oh) { d0 = od; has = true; }
+        }
     }
     const float nkc = p.nkc;
 
@@ -197,6 +206,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
             L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
         }
+        // per-row partial sums: shorter fp32 accumulation chains (error grows with the chain length)
+        float racc[4] = {0.f, 0.f, 0.f, 0.f}, rws[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = C0; c < C0 + WS + 3; ++c) {
             const float dsh = dq[c] - d0;
@@ -207,20 +218,24 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                     const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
                     const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
                     const float f = ex2_approx(fmaf(cdf, nkc, L[j]));
-                    acc[k] = fmaf(f, dsh, acc[k]);
-                    wsum[k] += f;
+                    racc[k] = fmaf(f, dsh, racc[k]);
+                    rws[k] += f;
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[k] += racc[k]; wsum[k] += rws[k]; }
     }
 
     // pass-1 weighted mean, in scaled tile-relative units
-    float m[4];
+    // the mean is kept as (d0, delta): e = (d - d0) - delta keeps full precision even when the tile
+    // spans metres of depth
+    float delta[4];
     bool any[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         any[k] = wsum[k] > 0.f;
-        m[k] = any[k] ? (acc[k] / wsum[k] + d0) : 0.f;
+        delta[k] = any[k] ? (acc[k] / wsum[k]) : 0.f;
     }
 
     const float e_thr = p.e_thr;
@@ -244,8 +259,10 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
             L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
         }
+        float rnum[4] = {0.f, 0.f, 0.f, 0.f}, rden[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = C0; c < C0 + WS + 3; ++c) {
+            const float dsh = dq[c] - d0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int j = c - C0 - k;
@@ -253,15 +270,17 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                     const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
                     const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
                     float arg = fmaf(cdf, nkc, L[j]);
-                    const float e = dq[c] - m[k];
+                    const float e = dsh - delta[k];
                     // fp32 expf(-(d-m)^2/(2 sd^2)) == 0  <=>  factor skipped (.cu:67-68)
                     if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
                     const float f = ex2_approx(arg);
-                    num[k] = fmaf(f, e, num[k]);
-                    den[k] += f;
+                    rnum[k] = fmaf(f, e, rnum[k]);
+                    rden[k] += f;
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { num[k] += rnum[k]; den[k] += rden[k]; }
     }
 
     // ---------------- epilogue: back to millimetres, 16-byte store
@@ -269,7 +288,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         // den > 0 whenever any tap is valid (weights are biased into the normal range)
-        const float r = (m[k] + num[k] / den[k]) * p.inv_sq;
+        const float r = ((delta[k] + num[k] / den[k]) + d0) * p.inv_sq;
         o[k] = any[k] ? (dref + r) : 0.f;
     }
     const int gy = y0 + ly, gx = x0 + 4 * lx;
@@ -359,10 +378,19 @@ jbf_generic_kernel(const JbfGenericParams gp_) {
     const int lx = tid % TW, ly = tid / TW;
     const int pc = (ly + R) * SP + lx + R;
     const uint32_t gpix = sG[pc];
-    const float dc = sD[pc];
-    const float d0 = (dc > -1.0e38f) ? dc : 0.f;
+    // accumulation origin: the centre sample, else the first sample of the window
+    float d0 = sD[pc];
+    if (!(d0 > -1.0e38f)) {
+        d0 = 0.f;
+        for (int t = 0; t < WS * WS; ++t) {
+            const int i = t / WS, j = t - i * WS;
+            const float d = sD[(ly + i) * SP + lx + j];
+            if (d > -1.0e38f) { d0 = d; break; }
+        }
+    }
     float acc = 0.f, wsum = 0.f;
-    for (int i = 0; i < WS; ++i)
+    for (int i = 0; i < WS; ++i) {
+        float racc = 0.f, rws = 0.f;
         for (int j = 0; j < WS; ++j) {
             const int q = (ly + i) * SP + lx + j;
             const float d = sD[q];
@@ -372,14 +400,18 @@ jbf_generic_kernel(const JbfGenericParams gp_) {
             float arg = sL[i * WS + j];
             if (gp_.use_color && cd <= gp_.cd_skip) arg = fmaf((float)cd, p.nkc, arg);
             const float f = ex2_approx(arg);
-            acc = fmaf(f, d - d0, acc);
-            wsum += f;
+            racc = fmaf(f, d - d0, racc);
+            rws += f;
         }
+        acc += racc;
+        wsum += rws;
+    }
     float o = 0.f;
     if (wsum > 0.f) {
-        const float m = acc / wsum + d0;
+        const float delta = acc / wsum;  // mean = d0 + delta
         float num = 0.f, den = 0.f;
-        for (int i = 0; i < WS; ++i)
+        for (int i = 0; i < WS; ++i) {
+            float rnum = 0.f, rden = 0.f;
             for (int j = 0; j < WS; ++j) {
                 const int q = (ly + i) * SP + lx + j;
                 const float d = sD[q];
@@ -388,13 +420,16 @@ jbf_generic_kernel(const JbfGenericParams gp_) {
                 const int cd = (int)__dp4a(ad, ad, 0u);
                 float arg = sL[i * WS + j];
                 if (gp_.use_color && cd <= gp_.cd_skip) arg = fmaf((float)cd, p.nkc, arg);
-                const float e = d - m;
+                const float e = (d - d0) - delta;
                 if (gp_.use_depth && !(fabsf(e) > p.e_thr)) arg = fmaf(-e, e, arg);
                 const float f = ex2_approx(arg);
-                num = fmaf(f, e, num);
-                den += f;
+                rnum = fmaf(f, e, rnum);
+                rden += f;
             }
-        o = (den > 0.f) ? dref + (m + num / den) * p.inv_sq : 0.f;
+            num += rnum;
+            den += rden;
+        }
+        o = (den > 0.f) ? dref + ((delta + num / den) + d0) * p.inv_sq : 0.f;
     }
     const int gx = x0 + lx, gy = y0 + ly;
     if (gx < p.width && gy < p.height)

@@ -65,7 +65,7 @@ def lib():
         L.orc_jbf_f32.argtypes = [C.c_int, C.c_int, _f32p, _u8p, _f32p, _f32p, C.c_int, C.c_float,
                                   C.c_float, C.c_int]
         L.orc_jbf_f64.argtypes = [C.c_int, C.c_int, _f32p, _u8p, _f32p, _f32p, C.c_void_p, C.c_int,
-                                  C.c_float, C.c_float, C.c_int]
+                                  C.c_float, C.c_float, C.c_int, C.c_double]
         L.orc_guided_fill_f32.argtypes = [C.c_int, C.c_int, _f32p, _u8p, C.c_void_p, _f32p, _f32p,
                                           C.c_int, C.c_float, C.c_float, C.c_int]
         L.orc_guided_fill_f64.argtypes = [C.c_int, C.c_int, _f32p, _u8p, C.c_void_p, _f32p, _f32p, C.c_void_p,
@@ -138,7 +138,7 @@ def presmooth(bgr, ksize=PRESMOOTH_KSIZE, sigma_color=PRESMOOTH_SIGMA_C, sigma_s
 
 
 def jbf(depth, guide, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_C, sigma_d=JBF_SIGMA_D,
-        precision="f32", threads=0, impl="oracle", return_mean=False):
+        precision="f32", threads=0, impl="oracle", return_mean=False, mean_shift_ulps=0.0):
     """Two-pass JBF kernel (JointBilateralFilter.cu:4-83) on an already smoothed guide.
 
     precision: "f32" (reference order, un-fused) or "f64" (exact-math with the fp32 skip rule).
@@ -160,8 +160,19 @@ def jbf(depth, guide, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_
         return out
     mean = np.empty((h, w), np.float64) if return_mean else None
     lib().orc_jbf_f64(w, h, depth, guide, lut, out, mean.ctypes.data if return_mean else None, window,
-                      sigma_c, sigma_d, threads)
+                      sigma_c, sigma_d, threads, float(mean_shift_ulps))
     return (out, mean) if return_mean else out
+
+
+def jbf_envelope(depth, guide, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_C, sigma_d=JBF_SIGMA_D,
+                 ulps=2.0, threads=0):
+    """fp64 oracle output plus the per-pixel half-width of the envelope its output spans when the
+    pass-1 mean moves by +-`ulps` fp32 ulps (the reference holds that mean in a float)."""
+    o, mean = jbf(depth, guide, window, sigma_s, sigma_c, sigma_d, "f64", threads, return_mean=True)
+    hi = jbf(depth, guide, window, sigma_s, sigma_c, sigma_d, "f64", threads, mean_shift_ulps=ulps)
+    lo = jbf(depth, guide, window, sigma_s, sigma_c, sigma_d, "f64", threads, mean_shift_ulps=-ulps)
+    band = np.maximum(np.abs(hi.astype(np.float64) - o), np.abs(lo.astype(np.float64) - o))
+    return o, band, mean
 
 
 def jbf_process(depth, bgr, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_C,

@@ -227,8 +227,13 @@ ORC_API void orc_jbf_f32(int width, int height, const float *depth, const uint8_
  * out > 0 exactly where a valid tap exists (mask == window dilation). */
 ORC_API void orc_jbf_f64(int width, int height, const float *depth, const uint8_t *guide,
                          const float *spatial, float *out, double *mean_out /*nullable*/,
-                         int window_size, float color_sigma, float depth_sigma, int n_threads)
+                         int window_size, float color_sigma, float depth_sigma, int n_threads,
+                         double mean_shift_ulps)
 {
+    /* mean_shift_ulps: the pass-1 mean is displaced by that many fp32 ulps before pass 2.  The
+     * reference keeps w_average in a float (JointBilateralFilter.cu:16,40), so every output in
+     * the envelope spanned by shifts of about +-1 ulp is a faithful evaluation of its formula;
+     * tests use +-2 ulps to bound the conditioning of each pixel ("Tolerance"). */
     int half = window_size / 2;
     double kc = (color_sigma != 0.0f) ? 1.0 / (2.0 * (double)color_sigma * (double)color_sigma) : 0.0;
     double kd = (depth_sigma != 0.0f) ? 1.0 / (2.0 * (double)depth_sigma * (double)depth_sigma) : 0.0;
@@ -244,6 +249,10 @@ ORC_API void orc_jbf_f64(int width, int height, const float *depth, const uint8_
                     if (!(wt > 0.0)) break;
                     m = a / wt;
                     if (mean_out) mean_out[y * width + x] = m;
+                    if (mean_shift_ulps != 0.0) {
+                        float mf = (float)m;
+                        m += mean_shift_ulps * (double)(nextafterf(mf, INFINITY) - mf);
+                    }
                 }
                 for (int i = -half; i <= half; i++) {
                     for (int j = -half; j <= half; j++) {
