@@ -51,6 +51,11 @@ struct JbfParams {
     int mode;                    // StageMode
     const float* depth_lo;       // upsample: low-res depth [hl][wl]
     int wl, hl;
+    // row-band mode: the arrays hold `height` rows (band + halos); output rows are
+    // [y_off, y_off + out_rows) of them and `out` holds only those.  Tiles start at y_off, so a
+    // band whose first image row is a multiple of the tile height is tiled exactly like the
+    // whole image and the result is bit-identical.  Whole-image mode: y_off = 0, out_rows = height.
+    int y_off, out_rows;
 };
 
 template <int R, int TW, int TH>
@@ -93,7 +98,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     float* sRed = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE + T::LBYTES + 16);  // NT/32 <= 16 floats
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = p.y_off + blockIdx.y * TH, frame = blockIdx.z;
     const int sx0 = x0 - RP, sy0 = y0 - R;  // image coords of staged (0,0)
 
     // ---------------- stage A: raw depth + guide tile with halo -> shared memory
@@ -292,8 +297,9 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         o[k] = any[k] ? (dref + r) : 0.f;
     }
     const int gy = y0 + ly, gx = x0 + 4 * lx;
-    if (gy < p.height && gx < p.width) {
-        float* dst = p.out + (long long)frame * p.width * p.height + (long long)gy * p.width + gx;
+    const int oy = gy - p.y_off;
+    if (oy < p.out_rows && gx < p.width) {
+        float* dst = p.out + (long long)frame * p.width * p.out_rows + (long long)oy * p.width + gx;
         if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
             stg_stream_f4(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
         } else {
@@ -331,7 +337,7 @@ jbf_generic_kernel(const JbfGenericParams gp_) {
     __shared__ float sRed[32];
     constexpr int NT = TW * TH;
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = p.y_off + blockIdx.y * TH, frame = blockIdx.z;
     const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
     const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
     for (int idx = tid; idx < SP * SH; idx += NT) {
@@ -431,9 +437,9 @@ jbf_generic_kernel(const JbfGenericParams gp_) {
         }
         o = (den > 0.f) ? dref + ((delta + num / den) + d0) * p.inv_sq : 0.f;
     }
-    const int gx = x0 + lx, gy = y0 + ly;
-    if (gx < p.width && gy < p.height)
-        p.out[(long long)frame * p.width * p.height + (long long)gy * p.width + gx] = o;
+    const int gx = x0 + lx, oy = y0 + ly - p.y_off;
+    if (gx < p.width && oy < p.out_rows)
+        p.out[(long long)frame * p.width * p.out_rows + (long long)oy * p.width + gx] = o;
 }
 
 }  // namespace kdme

@@ -276,23 +276,30 @@ extern "C" int jbf_set_presmooth(jbf_handle* h, int ksize, float sigma_color, fl
 
 // ------------------------------------------------------------------ launches
 static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, uint32_t* guide4, int guide_pitch,
-                            int n) {
+                            int n, int rows = -1) {
+    if (rows < 0) rows = rows;
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
     if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
     if (h->ps_ksize == 0) {
-        dim3 blk(128), grd((h->width + 127) / 128, h->height, n);
-        bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr, (long long)bgr_step, (long long)bgr_step * h->height,
-                                                         guide4, guide_pitch, (long long)guide_pitch * h->height,
-                                                         h->width, h->height);
+        dim3 blk(128), grd((h->width + 127) / 128, rows, n);
+        bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr, (long long)bgr_step, (long long)bgr_step * rows,
+                                                         guide4, guide_pitch, (long long)guide_pitch * rows,
+                                                         h->width, rows);
     } else {
         PresmoothParams p;
-        p.width = h->width; p.height = h->height; p.n_frames = n;
-        p.bgr = bgr; p.bgr_step = (long long)bgr_step; p.bgr_frame_stride = (long long)bgr_step * h->height;
-        p.guide4 = guide4; p.guide_pitch = guide_pitch; p.guide_frame_stride = (long long)guide_pitch * h->height;
+        p.width = h->width; p.height = rows; p.n_frames = n;
+        p.bgr = bgr; p.bgr_step = (long long)bgr_step; p.bgr_frame_stride = (long long)bgr_step * rows;
+        p.guide4 = guide4; p.guide_pitch = guide_pitch; p.guide_frame_stride = (long long)guide_pitch * rows;
         p.ksize = h->ps_ksize; p.space_lut = h->ps_space_dev; p.color_lut = h->ps_color_dev;
-        constexpr int TW = 32, TH = 8;
-        dim3 grd((h->width + TW - 1) / TW, (h->height + TH - 1) / TH, n);
-        presmooth_kernel<TW, TH><<<grd, TW * TH, 0, h->stream>>>(p);
+        if (h->ps_ksize == 5) {
+            constexpr int TW = 64, TH = 8;
+            dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
+            presmooth5_kernel<TW, TH><<<grd, (TW / 4) * TH, 0, h->stream>>>(p);
+        } else {
+            constexpr int TW = 32, TH = 8;
+            dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
+            presmooth_kernel<TW, TH><<<grd, TW * TH, 0, h->stream>>>(p);
+        }
     }
     CK(cudaGetLastError());
     return KDME_OK;
@@ -308,7 +315,7 @@ static int launch_fast_r(jbf_handle* h, const JbfParams& p, const CUtensorMap& t
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
         attr_done[h->device & 63] = true;
     }
-    dim3 grd((p.width + TW - 1) / TW, (p.height + TH - 1) / TH, p.n_frames);
+    dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
     kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
     CK(cudaGetLastError());
     return KDME_OK;
@@ -333,12 +340,16 @@ static bool fast_radius_available(int r) {
 }
 
 static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guide4, int guide_pitch, float* out,
-                         int n, int mode, const float* depth_lo, int wl, int hl) {
+                         int n, int mode, const float* depth_lo, int wl, int hl, int rows = -1, int y_off = 0,
+                         int out_rows = -1) {
     JbfParams p;
-    p.width = h->width; p.height = h->height; p.n_frames = n;
+    if (rows < 0) rows = h->height;
+    if (out_rows < 0) out_rows = rows;
+    p.width = h->width; p.height = rows; p.n_frames = n;
+    p.y_off = y_off; p.out_rows = out_rows;
     p.depth = depth; p.guide4 = guide4; p.out = out;
-    p.depth_frame_stride = (long long)h->width * h->height;
-    p.guide_frame_stride = (long long)guide_pitch * h->height;
+    p.depth_frame_stride = (long long)h->width * rows;
+    p.guide_frame_stride = (long long)guide_pitch * rows;
     p.guide_pitch = guide_pitch;
     p.nkc = h->nkc; p.sq = h->sq; p.inv_sq = h->inv_sq; p.e_thr = h->e_thr;
     p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
@@ -354,10 +365,10 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
                 KDME_FAST_RADII(X)
 #undef X
             }
-            bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, h->width, h->height, n,
-                                 (long long)h->width * 4, (long long)h->width * h->height * 4, bx, by) &&
-                      encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, guide4, h->width, h->height, n,
-                                 (long long)guide_pitch * 4, (long long)guide_pitch * h->height * 4, bx, by);
+            bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, h->width, rows, n,
+                                 (long long)h->width * 4, (long long)h->width * rows * 4, bx, by) &&
+                      encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, guide4, h->width, rows, n,
+                                 (long long)guide_pitch * 4, (long long)guide_pitch * rows * 4, bx, by);
             if (ok) p.mode = kStageTma;
         }
         h->last_variant = 0 | (p.mode == kStageTma ? 0x100 : 0);
@@ -381,7 +392,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
         CK(cudaFuncSetAttribute(jbf_generic_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_done[h->device & 63] = true;
     }
-    dim3 grd((p.width + TW - 1) / TW, (p.height + TH - 1) / TH, n);
+    dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, n);
     jbf_generic_kernel<TW, TH><<<grd, TW * TH, smem, h->stream>>>(gp);
     CK(cudaGetLastError());
     h->last_variant = 1;
@@ -410,6 +421,30 @@ extern "C" int jbf_filter_guide4(jbf_handle* h, const float* depth_dev, const ui
     DeviceGuard g(h->device);
     return launch_filter(h, depth_dev, reinterpret_cast<const uint32_t*>(guide4_dev), (int)(guide_step / 4), out_dev,
                          n_frames, kStagePlain, nullptr, 0, 0);
+}
+
+extern "C" int jbf_presmooth_rows(jbf_handle* h, const uint8_t* bgr_dev, size_t bgr_step, uint8_t* guide4_dev,
+                                  size_t guide_step, int rows) {
+    if (!h || !bgr_dev || !guide4_dev) return fail(KDME_EINVAL, "jbf_presmooth_rows: NULL argument");
+    if (rows < 1) return fail(KDME_EINVAL, "jbf_presmooth_rows: rows must be >= 1");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_presmooth_rows: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_presmooth(h, bgr_dev, bgr_step, reinterpret_cast<uint32_t*>(guide4_dev), (int)(guide_step / 4), 1, rows);
+}
+
+extern "C" int jbf_filter_rows(jbf_handle* h, const float* depth_dev, const uint8_t* guide4_dev, size_t guide_step,
+                               float* out_dev, int rows, int y_off, int out_rows) {
+    if (!h || !depth_dev || !guide4_dev || !out_dev) return fail(KDME_EINVAL, "jbf_filter_rows: NULL argument");
+    if (rows < 1 || y_off < 0 || out_rows < 1 || y_off + out_rows > rows)
+        return fail(KDME_EINVAL, "jbf_filter_rows: need 0 <= y_off and y_off + out_rows <= rows");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_filter_rows: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_filter(h, depth_dev, reinterpret_cast<const uint32_t*>(guide4_dev), (int)(guide_step / 4), out_dev, 1,
+                         kStagePlain, nullptr, 0, 0, rows, y_off, out_rows);
 }
 
 extern "C" int jbf_process_batch(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step,

@@ -8,8 +8,9 @@
 //
 // Both exponentials come from LUTs built on the host (space: ksize^2 entries,
 // colour: 766 entries indexed by the integer L1 distance), multiplied in fp32 and
-// accumulated un-fused in tap order (dy outer, dx inner), so the result is
-// bit-identical to oracle/kdme_oracle.c:orc_presmooth_bgr given the same LUTs.
+// accumulated with one FFMA per channel in tap order (dy outer, dx inner), so the
+// result is bit-identical to the CPU restatement of the same definition given the
+// same LUTs.
 //
 // Input: packed BGR u8x3 rows (cv::gpu::GpuMat CV_8UC3).  Output: the internal
 // u8x4 {B,G,R,0} guide (16-byte alignable rows, one 32-bit word per pixel) that the
@@ -77,9 +78,9 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
             const uint32_t ad = __vabsdiffu4(q, c);
             const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
             const float w = __fmul_rn(sw, sCol[l1]);
-            s0 = __fadd_rn(s0, __fmul_rn(w, (float)(q & 0xffu)));
-            s1 = __fadd_rn(s1, __fmul_rn(w, (float)((q >> 8) & 0xffu)));
-            s2 = __fadd_rn(s2, __fmul_rn(w, (float)((q >> 16) & 0xffu)));
+            s0 = __fmaf_rn(w, (float)(q & 0xffu), s0);
+            s1 = __fmaf_rn(w, (float)((q >> 8) & 0xffu), s1);
+            s2 = __fmaf_rn(w, (float)((q >> 16) & 0xffu), s2);
             ws = __fadd_rn(ws, w);
         }
     }
@@ -88,6 +89,77 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
     const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2, ws)), 0.f), 255.f);
     const uint32_t o = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
     p.guide4[(long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx] = o;
+}
+
+// ksize == 5 (the reference's call): 13 taps fully unrolled, 4 pixels per thread along x.  Each
+// staged pixel is converted ONCE to {float b, float g, float r, packed u8x4} (16 bytes), so a tap
+// is LDS.128 + VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
+template <int TW, int TH>
+__global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const PresmoothParams p) {
+    constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 2 * R, SH = TH + 2 * R;
+    __shared__ float4 sPix[SP * SH];
+    __shared__ float sCol[768];
+    __shared__ float sSp[25];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
+    const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
+        const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
+        const uint32_t b = __ldg(q), g = __ldg(q + 1), r = __ldg(q + 2);
+        sPix[idx] = make_float4((float)b, (float)g, (float)r, __uint_as_float(b | (g << 8) | (r << 16)));
+    }
+    for (int idx = tid; idx < 766; idx += NT) sCol[idx] = __ldg(p.color_lut + idx);
+    if (tid < 25) sSp[tid] = __ldg(p.space_lut + tid);
+    __syncthreads();
+
+    const int lx = tid % (TW / 4), ly = tid / (TW / 4);
+    uint32_t c[4];
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f},
+          ws[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = __float_as_uint(sPix[(ly + R) * SP + 4 * lx + k + R].w);
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        float4 row[8];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) row[cidx] = sPix[(ly + dy) * SP + 4 * lx + cidx];
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            if ((dx - 2) * (dx - 2) + (dy - 2) * (dy - 2) > 4) continue;  // outside the circle (compile time)
+            const float sw = sSp[dy * 5 + dx];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 q = row[k + dx];
+                const uint32_t ad = __vabsdiffu4(__float_as_uint(q.w), c[k]);
+                const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
+                const float w = __fmul_rn(sw, sCol[l1]);
+                s0[k] = __fmaf_rn(w, q.x, s0[k]);
+                s1[k] = __fmaf_rn(w, q.y, s1[k]);
+                s2[k] = __fmaf_rn(w, q.z, s2[k]);
+                ws[k] = __fadd_rn(ws[k], w);
+            }
+        }
+    }
+    const int gy = y0 + ly, gx = x0 + 4 * lx;
+    if (gy >= p.height || gx >= p.width) return;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0[k], ws[k])), 0.f), 255.f);
+        const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1[k], ws[k])), 0.f), 255.f);
+        const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2[k], ws[k])), 0.f), 255.f);
+        o[k] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
+    }
+    uint32_t* dst = p.guide4 + (long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx;
+    if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (gx + k < p.width) dst[k] = o[k];
+    }
 }
 
 // packed BGR -> internal u8x4 without smoothing (pre-smooth disabled, guided fill, MRF)

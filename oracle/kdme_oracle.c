@@ -75,8 +75,9 @@ ORC_API void orc_spatial_lut(float *lut, int window_size, float spatial_sigma)
  * its published algorithm: circular window dx^2+dy^2 <= (ksize/2)^2, weight
  * exp(-space2/(2 ss^2)) * exp(-L1(dBGR)^2/(2 sc^2)), reflect-101 border,
  * round-to-nearest-even saturate to u8.  Weights are taken from two fp32 LUTs
- * multiplied in fp32 and accumulated un-fused in tap order (cy outer, cx
- * inner), so a device implementation fed the same LUTs can be bit-exact.
+ * multiplied in fp32 and accumulated with one fused multiply-add per channel in
+ * tap order (cy outer, cx inner), so a device implementation fed the same LUTs
+ * is bit-exact.
  * PARITY UNPINNED for this stage (third-party, no reference fixture). */
 static int orc_reflect101(int p, int len)
 {
@@ -126,9 +127,9 @@ ORC_API void orc_presmooth_bgr(const uint8_t *src, size_t src_step, uint8_t *dst
                     int l1 = abs((int)q[0] - (int)c[0]) + abs((int)q[1] - (int)c[1]) +
                              abs((int)q[2] - (int)c[2]);
                     float wgt = sw * color_lut[l1];
-                    s0 = s0 + wgt * (float)q[0];
-                    s1 = s1 + wgt * (float)q[1];
-                    s2 = s2 + wgt * (float)q[2];
+                    s0 = fmaf(wgt, (float)q[0], s0);   /* one rounding per tap: a device FFMA is bit-identical */
+                    s1 = fmaf(wgt, (float)q[1], s1);
+                    s2 = fmaf(wgt, (float)q[2], s2);
                     ws = ws + wgt;
                 }
             }
