@@ -277,7 +277,7 @@ extern "C" int jbf_set_presmooth(jbf_handle* h, int ksize, float sigma_color, fl
 // ------------------------------------------------------------------ launches
 static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, uint32_t* guide4, int guide_pitch,
                             int n, int rows = -1) {
-    if (rows < 0) rows = rows;
+    if (rows < 0) rows = h->height;
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
     if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
     if (h->ps_ksize == 0) {
