@@ -59,12 +59,23 @@ __global__ void __launch_bounds__(256) buf2d_kernel(float* __restrict__ buf, con
             b4[1] = make_float4(c.x, (float)((px + 2) / width), c.z, (float)((px + 3) / width));
         } else if (OP == kBufUpdate) {
             float4 a = b4[0], c = b4[1];
-            for (int f = 0; f < n_frames; ++f) {
-                const float4 d = ldg_stream_f4(reinterpret_cast<const float4*>(data + (long long)f * n) + qd);
-                update_weighted(a.x, a.y, d.x);
-                update_weighted(a.z, a.w, d.y);
-                update_weighted(c.x, c.y, d.z);
-                update_weighted(c.z, c.w, d.w);
+            // frames are applied in order (the update is a recurrence per pixel) but their loads are
+            // independent: issue 8 at a time so the pass stays bandwidth- rather than latency-bound
+            constexpr int PF = 8;
+            for (int f0 = 0; f0 < n_frames; f0 += PF) {
+                float4 d[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (f0 + u < n_frames)
+                        d[u] = ldg_stream_f4(reinterpret_cast<const float4*>(data + (long long)(f0 + u) * n) + qd);
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (f0 + u < n_frames) {
+                        update_weighted(a.x, a.y, d[u].x);
+                        update_weighted(a.z, a.w, d[u].y);
+                        update_weighted(c.x, c.y, d[u].z);
+                        update_weighted(c.z, c.w, d[u].w);
+                    }
             }
             b4[0] = a;
             b4[1] = c;

@@ -102,7 +102,7 @@ struct jbf_handle {
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
-    bool force_no_tma = false;
+    bool force_no_tma = false, force_big_tiles = false;
     int last_variant = 0;
     // host pipeline (jbf_process_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -180,6 +180,7 @@ static int build_tables(jbf_handle* h) {
               (h->nkc < -1e-20f) && std::isfinite(h->sq) && h->sq > 0.f && fast_radius_available(h->radius);
     if (getenv("KDME_FORCE_GENERIC")) h->fast = false;
     h->force_no_tma = getenv("KDME_NO_TMA") != nullptr;
+    h->force_big_tiles = getenv("KDME_BIG_TILES") != nullptr;
     return KDME_OK;
 }
 
@@ -305,9 +306,11 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
     return KDME_OK;
 }
 
-template <int R>
-static int launch_fast_r(jbf_handle* h, const JbfParams& p, const CUtensorMap& tmd, const CUtensorMap& tmg) {
-    constexpr int TW = 64, TH = 16, MINB = 2;
+// One (radius, tile height) instantiation: encode the TMA maps for its box and launch.
+template <int R, int TH>
+static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
+    constexpr int TW = 64;
+    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : 4;
     using T = JbfTile<R, TW, TH>;
     auto kern = jbf_fast_kernel<R, TW, TH, MINB>;
     static bool attr_done[64] = {};
@@ -315,16 +318,20 @@ static int launch_fast_r(jbf_handle* h, const JbfParams& p, const CUtensorMap& t
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
         attr_done[h->device & 63] = true;
     }
+    CUtensorMap tmd, tmg;
+    memset(&tmd, 0, sizeof(tmd)); memset(&tmg, 0, sizeof(tmg));
+    if (want_tma) {
+        bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.depth, p.width, rows, p.n_frames,
+                             (long long)p.width * 4, (long long)p.width * rows * 4, T::SP, T::SH) &&
+                  encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.guide4, p.width, rows, p.n_frames,
+                             (long long)p.guide_pitch * 4, (long long)p.guide_pitch * rows * 4, T::SP, T::SH);
+        if (ok) p.mode = kStageTma;
+    }
+    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0);
     dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
     kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
     CK(cudaGetLastError());
     return KDME_OK;
-}
-
-template <int R>
-static void tile_box(int& bx, int& by) {
-    using T = JbfTile<R, 64, 16>;
-    bx = T::SP; by = T::SH;
 }
 
 #define KDME_FAST_RADII(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15)
@@ -355,25 +362,17 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
     if (h->fast) {
         p.ltab = h->ltab_dev;
-        CUtensorMap tmd, tmg;
-        memset(&tmd, 0, sizeof(tmd)); memset(&tmg, 0, sizeof(tmg));
-        if (p.mode == kStagePlain && !h->force_no_tma && (h->width % 4 == 0) && (guide_pitch % 4 == 0) &&
-            ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) && ((reinterpret_cast<uintptr_t>(guide4) & 15) == 0)) {
-            int bx = 0, by = 0;
-            switch (h->radius) {
-#define X(R) case R: tile_box<R>(bx, by); break;
-                KDME_FAST_RADII(X)
-#undef X
-            }
-            bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, depth, h->width, rows, n,
-                                 (long long)h->width * 4, (long long)h->width * rows * 4, bx, by) &&
-                      encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, guide4, h->width, rows, n,
-                                 (long long)guide_pitch * 4, (long long)guide_pitch * rows * 4, bx, by);
-            if (ok) p.mode = kStageTma;
-        }
-        h->last_variant = 0 | (p.mode == kStageTma ? 0x100 : 0);
+        const bool want_tma = p.mode == kStagePlain && !h->force_no_tma && (h->width % 4 == 0) &&
+                              (guide_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(guide4) & 15) == 0);
+        // Small launches (a single Kinect frame is 300 tiles of 64x16 on 148 SMs) use 64x8 tiles: twice the
+        // CTAs, so the SMs are loaded evenly.  Whole-frame and band results do not depend on the choice of
+        // tile for parity, but bit-identity between band and whole-frame needs the same tile: bands pass
+        // y_off/out_rows and always use 64x16.
+        const long long ctas16 = (long long)((h->width + 63) / 64) * ((out_rows + 15) / 16) * n;
+        const bool small_tiles = (ctas16 < 4LL * 148 * 3) && (rows == out_rows) && !h->force_big_tiles;
         switch (h->radius) {
-#define X(R) case R: return launch_fast_r<R>(h, p, tmd, tmg);
+#define X(R) case R: return small_tiles ? launch_fast_rt<R, 8>(h, p, want_tma, rows) : launch_fast_rt<R, 16>(h, p, want_tma, rows);
             KDME_FAST_RADII(X)
 #undef X
         }
@@ -581,7 +580,7 @@ extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
     return h->smooth_bgr;
 }
 
-extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x100)) : -1; }
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x300)) : -1; }
 
 // ------------------------------------------------------------------ MRF (next row f1)
 extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,

@@ -92,23 +92,30 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
 }
 
 // ksize == 5 (the reference's call): 13 taps fully unrolled, 4 pixels per thread along x.  Each
-// staged pixel is converted ONCE to {float b, float g, float r, packed u8x4} (16 bytes), so a tap
-// is LDS.128 + VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
+// staged pixel is converted ONCE to float b, g, r and a packed u8x4 word, kept as four shared-memory
+// planes so a thread fetches its 8-column row segment with conflict-free 16-byte LDS; a tap is then
+// VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
 template <int TW, int TH>
 __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const PresmoothParams p) {
-    constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 2 * R, SH = TH + 2 * R;
-    __shared__ float4 sPix[SP * SH];
+    constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
+    constexpr int XO = 4 - R;                                               // first used column of a staged row
+    __shared__ __align__(16) float sB[SP * SH];
+    __shared__ __align__(16) float sG[SP * SH];
+    __shared__ __align__(16) float sR[SP * SH];
+    __shared__ __align__(16) uint32_t sP[SP * SH];
     __shared__ float sCol[768];
     __shared__ float sSp[25];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
     const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
-    for (int idx = tid; idx < SP * SH; idx += NT) {
-        int sy = idx / SP, sx = idx - sy * SP;
+    constexpr int SW = TW + 2 * R;   // staged (used) columns per row
+    for (int idx = tid; idx < SW * SH; idx += NT) {
+        int sy = idx / SW, sx = idx - sy * SW;
         int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
         const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
         const uint32_t b = __ldg(q), g = __ldg(q + 1), r = __ldg(q + 2);
-        sPix[idx] = make_float4((float)b, (float)g, (float)r, __uint_as_float(b | (g << 8) | (r << 16)));
+        const int o = sy * SP + XO + sx;
+        sB[o] = (float)b; sG[o] = (float)g; sR[o] = (float)r; sP[o] = b | (g << 8) | (r << 16);
     }
     for (int idx = tid; idx < 766; idx += NT) sCol[idx] = __ldg(p.color_lut + idx);
     if (tid < 25) sSp[tid] = __ldg(p.space_lut + tid);
@@ -118,26 +125,40 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     uint32_t c[4];
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f},
           ws[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) c[k] = __float_as_uint(sPix[(ly + R) * SP + 4 * lx + k + R].w);
+    {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (ly + R) * SP + 4 * lx + 4);
+        c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+    }
 #pragma unroll
     for (int dy = 0; dy < 5; ++dy) {
-        float4 row[8];
+        // columns [4*lx, 4*lx + 12) of the staged row: pixel k, tap dx sits at local column XO + k + dx
+        float rb[12], rg[12], rr[12];
+        uint32_t rp[12];
+        const int base = (ly + dy) * SP + 4 * lx;
 #pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) row[cidx] = sPix[(ly + dy) * SP + 4 * lx + cidx];
+        for (int v = 0; v < 3; ++v) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sB + base + 4 * v);
+            const float4 g4 = *reinterpret_cast<const float4*>(sG + base + 4 * v);
+            const float4 r4 = *reinterpret_cast<const float4*>(sR + base + 4 * v);
+            const uint4 p4 = *reinterpret_cast<const uint4*>(sP + base + 4 * v);
+            rb[4 * v] = b4.x; rb[4 * v + 1] = b4.y; rb[4 * v + 2] = b4.z; rb[4 * v + 3] = b4.w;
+            rg[4 * v] = g4.x; rg[4 * v + 1] = g4.y; rg[4 * v + 2] = g4.z; rg[4 * v + 3] = g4.w;
+            rr[4 * v] = r4.x; rr[4 * v + 1] = r4.y; rr[4 * v + 2] = r4.z; rr[4 * v + 3] = r4.w;
+            rp[4 * v] = p4.x; rp[4 * v + 1] = p4.y; rp[4 * v + 2] = p4.z; rp[4 * v + 3] = p4.w;
+        }
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
             if ((dx - 2) * (dx - 2) + (dy - 2) * (dy - 2) > 4) continue;  // outside the circle (compile time)
             const float sw = sSp[dy * 5 + dx];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float4 q = row[k + dx];
-                const uint32_t ad = __vabsdiffu4(__float_as_uint(q.w), c[k]);
+                const int col = XO + k + dx;
+                const uint32_t ad = __vabsdiffu4(rp[col], c[k]);
                 const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
                 const float w = __fmul_rn(sw, sCol[l1]);
-                s0[k] = __fmaf_rn(w, q.x, s0[k]);
-                s1[k] = __fmaf_rn(w, q.y, s1[k]);
-                s2[k] = __fmaf_rn(w, q.z, s2[k]);
+                s0[k] = __fmaf_rn(w, rb[col], s0[k]);
+                s1[k] = __fmaf_rn(w, rg[col], s1[k]);
+                s2[k] = __fmaf_rn(w, rr[col], s2[k]);
                 ws[k] = __fadd_rn(ws[k], w);
             }
         }

@@ -98,7 +98,11 @@ def test_filter_matches_f64_oracle_tma_path(w, h, radius):
     out, variant = gpu_filter(depth, guide, radius)
     assert variant & 0x100, "expected the TMA-staged fast kernel"
     assert (variant & 1) == 0
-    check_against_f64(out, depth, guide, 2 * radius + 1, 70.0, 50.0, 20.0, f"{w}x{h}")
+    check_against_f64(out, depth, guide, 2 * radius + 1, 70.0, 50.0, 20.0, f"{w}x{h} variant=0x{variant:x}")
+    # the other tile shape (64x16 instead of the 64x8 picked for small launches) must pass the same bound
+    out_big, vbig = gpu_filter(depth, guide, radius, env={"KDME_BIG_TILES": "1"})
+    assert not (vbig & 0x200)
+    check_against_f64(out_big, depth, guide, 2 * radius + 1, 70.0, 50.0, 20.0, f"{w}x{h} variant=0x{vbig:x}")
 
 
 @pytest.mark.parametrize("w,h,radius", [(70, 50, 2), (70, 50, 7), (33, 17, 3), (5, 3, 2), (1, 1, 2), (101, 67, 5)])
