@@ -62,6 +62,13 @@ __global__ void __launch_bounds__(256) buf2d_kernel(float* __restrict__ buf, con
             // frames are applied in order (the update is a recurrence per pixel) but their loads are
             // independent: issue 8 at a time so the pass stays bandwidth- rather than latency-bound
             constexpr int PF = 8;
+            if (n_frames == 1) {  // the per-frame call of the reference (Buffer2D.cu:116-120): pure streaming
+                const float4 d = ldg_stream_f4(reinterpret_cast<const float4*>(data) + qd);
+                update_weighted(a.x, a.y, d.x);
+                update_weighted(a.z, a.w, d.y);
+                update_weighted(c.x, c.y, d.z);
+                update_weighted(c.z, c.w, d.w);
+            } else
             for (int f0 = 0; f0 < n_frames; f0 += PF) {
                 float4 d[PF];
 #pragma unroll

@@ -109,13 +109,30 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
     const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
     constexpr int SW = TW + 2 * R;   // staged (used) columns per row
-    for (int idx = tid; idx < SW * SH; idx += NT) {
-        int sy = idx / SW, sx = idx - sy * SW;
-        int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
-        const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
-        const uint32_t b = __ldg(q), g = __ldg(q + 1), r = __ldg(q + 2);
-        const int o = sy * SP + XO + sx;
-        sB[o] = (float)b; sG[o] = (float)g; sR[o] = (float)r; sP[o] = b | (g << 8) | (r << 16);
+    constexpr int NIT = (SW * SH + NT - 1) / NT;
+    {   // all byte loads of the thread are issued before the first use (memory-level parallelism)
+        uint32_t vb[NIT], vg[NIT], vr[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = tid + it * NT;
+            vb[it] = vg[it] = vr[it] = 0u;
+            if (idx < SW * SH) {
+                int sy = idx / SW, sx = idx - sy * SW;
+                int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
+                const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
+                vb[it] = __ldg(q); vg[it] = __ldg(q + 1); vr[it] = __ldg(q + 2);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = tid + it * NT;
+            if (idx < SW * SH) {
+                int sy = idx / SW, sx = idx - sy * SW;
+                const int o = sy * SP + XO + sx;
+                sB[o] = (float)vb[it]; sG[o] = (float)vg[it]; sR[o] = (float)vr[it];
+                sP[o] = vb[it] | (vg[it] << 8) | (vr[it] << 16);
+            }
+        }
     }
     for (int idx = tid; idx < 766; idx += NT) sCol[idx] = __ldg(p.color_lut + idx);
     if (tid < 25) sSp[tid] = __ldg(p.space_lut + tid);
