@@ -113,6 +113,27 @@ def fp32_peak():
     return FP32_NOMINAL_TFLOPS, "nominal (148 SM x 128 FMA/clk x 2 x 1.965 GHz)", None
 
 
+def measured_traffic(pixels_per_launch: int):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
+    (dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_jbf_fast_r7_*.ncu.txt), scaled to this
+    launch's pixel count (traffic is proportional to pixels: every CTA stages one 64x16 tile + halo)."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_jbf_fast_r7_*.ncu.txt")))
+    if not files:
+        return None, None
+    txt = open(files[-1]).read()
+    rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
+    wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)
+    grid = re.search(r"launch__grid_size\s+([0-9]+)", txt)
+    if not (rd and wr and grid):
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = float(rd.group(1)) * scale[rd.group(2)] + float(wr.group(1)) * scale[wr.group(2)]
+    prof_pixels = int(grid.group(1)) * 64 * 16
+    return total * pixels_per_launch / prof_pixels, os.path.relpath(files[-1], ROOT)
+
+
 def cpu_baseline(budget_s: float, frames_np=None):
     """The reference's own kernel text on the host cores (oracle/_ref), else the C restatement (port)."""
     import numpy as np
@@ -128,7 +149,7 @@ def cpu_baseline(budget_s: float, frames_np=None):
     g = oracle.presmooth(c)
     oracle.jbf(d, g, 2 * RADIUS + 1, *SIGMAS, precision="f32", impl=impl, threads=cores)
     t1 = time.perf_counter() - t0
-    n = max(1, min(64, int(budget_s / max(t1, 1e-3)) - 1))
+    n = max(1, min(512, int(budget_s / max(t1, 1e-3)) - 1))
     t0 = time.perf_counter()
     for i in range(n):
         g = oracle.presmooth(c)
@@ -285,6 +306,7 @@ def main():
         px_per_launch = args.chunk * W * H
         ach_tf = px_per_launch * FLOP_PER_PIXEL / (kern_ms * 1e-3) / 1e12
         ach_gbs = px_per_launch * BYTES_PER_PIXEL / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(px_per_launch)
         line = {
             "metric": "JBF Mpixel/s at 640x480 r=7", "value": value, "unit": "Mpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
@@ -301,7 +323,8 @@ def main():
                 "kernel_ms_per_launch": kern_ms, "kernel_mpixel_s": px_per_launch / (kern_ms * 1e-3) / 1e6,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                         "peak_source": peaks_kind + " (MEASURED_PEAKS.json)", "bytes_per_pixel": BYTES_PER_PIXEL},
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": px_per_launch * BYTES_PER_PIXEL,
                 "note": "the path is FP32/MUFU-issue bound (intensity 675 flop/B vs balance ~11), see DESIGN.md",
             },
             "microbench": micro,
