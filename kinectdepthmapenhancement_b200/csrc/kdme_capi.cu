@@ -82,6 +82,7 @@ static bool encode_map(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 }
 
 // ------------------------------------------------------------------ JBF handle
+constexpr int kPipeDepth = 3;  // device slots of the host pipeline (jbf_process_host)
 struct jbf_handle {
     int width = 0, height = 0, radius = 0, max_batch = 1, device = 0;
     float sigma_s = 0, sigma_c = 0, sigma_d = 0;
@@ -106,11 +107,12 @@ struct jbf_handle {
     int last_variant = 0;
     // host pipeline (jbf_process_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    float* pipe_depth[2] = {nullptr, nullptr};
-    uint8_t* pipe_bgr[2] = {nullptr, nullptr};
-    float* pipe_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kPipeDepth] = {}, ev_done[kPipeDepth] = {}, ev_free[kPipeDepth] = {};
+    float* pipe_depth[kPipeDepth] = {};
+    uint8_t* pipe_bgr[kPipeDepth] = {};
+    float* pipe_out[kPipeDepth] = {};
     size_t pipe_bgr_step = 0;
+    int pipe_chunk = 1;
 };
 
 static bool fast_radius_available(int r);
@@ -253,7 +255,7 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->ltab_generic_dev);
     cudaFree(h->ps_space_dev);
     cudaFree(h->ps_color_dev);
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kPipeDepth; b++) {
         cudaFree(h->pipe_depth[b]); cudaFree(h->pipe_bgr[b]); cudaFree(h->pipe_out[b]);
         if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
@@ -480,24 +482,31 @@ extern "C" int jbf_upsample(jbf_handle* h, const float* depth_lo_dev, int wl, in
     return launch_filter(h, nullptr, h->guide4, h->guide_pitch, out_hi_dev, 1, kStageUpsample, depth_lo_dev, wl, hl);
 }
 
+// Host pipeline: kPipeDepth device slots of pipe_chunk frames each; H2D, compute and D2H run on three
+// streams so that, in steady state, the upload of chunk c+1 and the download of chunk c-1 overlap the
+// filter of chunk c.  Small chunks keep the fill/drain bubble short.
 static int ensure_pipe(jbf_handle* h, size_t bgr_step) {
     if (h->s_h2d && h->pipe_bgr_step == bgr_step) return KDME_OK;
     if (h->s_h2d && h->pipe_bgr_step != bgr_step) {
-        for (int b = 0; b < 2; b++) { cudaFree(h->pipe_bgr[b]); h->pipe_bgr[b] = nullptr; }
+        for (int b = 0; b < kPipeDepth; b++) { cudaFree(h->pipe_bgr[b]); h->pipe_bgr[b] = nullptr; }
     }
     const size_t plane = (size_t)h->width * h->height;
     if (!h->s_h2d) {
+        // ~5 Mpixel per chunk (16 Kinect frames): enough CTAs to fill the GPU, short pipeline bubble
+        long long want = (5LL << 20) / (long long)plane;
+        if (want < 1) want = 1;
+        h->pipe_chunk = (int)((want < h->max_batch) ? want : h->max_batch);
         CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < kPipeDepth; b++) {
             CK(cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
-            CK(cudaMalloc(&h->pipe_depth[b], plane * h->max_batch * sizeof(float)));
-            CK(cudaMalloc(&h->pipe_out[b], plane * h->max_batch * sizeof(float)));
+            CK(cudaMalloc(&h->pipe_depth[b], plane * h->pipe_chunk * sizeof(float)));
+            CK(cudaMalloc(&h->pipe_out[b], plane * h->pipe_chunk * sizeof(float)));
         }
     }
-    for (int b = 0; b < 2; b++) CK(cudaMalloc(&h->pipe_bgr[b], bgr_step * h->height * h->max_batch));
+    for (int b = 0; b < kPipeDepth; b++) CK(cudaMalloc(&h->pipe_bgr[b], bgr_step * h->height * h->pipe_chunk));
     h->pipe_bgr_step = bgr_step;
     return KDME_OK;
 }
@@ -513,21 +522,18 @@ extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const ui
     if (rc != KDME_OK) return rc;
     const size_t plane = (size_t)h->width * h->height;
     const size_t bgr_frame = bgr_step * h->height;
-    // order the pipeline after work already queued on the handle's stream
     int chunk = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch, ++chunk) {
-        const int n = (n_frames - f0 < h->max_batch) ? (n_frames - f0) : h->max_batch;
-        const int b = chunk & 1;
-        if (chunk >= 2) {
-            CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[b], 0));  // inputs of chunk-2 consumed
-        }
+    for (int f0 = 0; f0 < n_frames; f0 += h->pipe_chunk, ++chunk) {
+        const int n = (n_frames - f0 < h->pipe_chunk) ? (n_frames - f0) : h->pipe_chunk;
+        const int b = chunk % kPipeDepth;
+        if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[b], 0));  // slot inputs consumed
         CK(cudaMemcpyAsync(h->pipe_depth[b], depth_host + (size_t)f0 * plane, plane * n * sizeof(float),
                            cudaMemcpyHostToDevice, h->s_h2d));
         CK(cudaMemcpyAsync(h->pipe_bgr[b], bgr_host + (size_t)f0 * bgr_frame, bgr_frame * n, cudaMemcpyHostToDevice,
                            h->s_h2d));
         CK(cudaEventRecord(h->ev_in[b], h->s_h2d));
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
-        if (chunk >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));  // out[b] drained
+        if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));  // slot output drained
         rc = launch_presmooth(h, h->pipe_bgr[b], bgr_step, h->guide4, h->guide_pitch, n);
         if (rc != KDME_OK) return rc;
         rc = launch_filter(h, h->pipe_depth[b], h->guide4, h->guide_pitch, h->pipe_out[b], n, kStagePlain, nullptr, 0, 0);
