@@ -142,6 +142,18 @@ int jbf_mrf(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_
 int kdme_projective_to_real(const float *depth_dev, float *xyz_dev, int width, int height, float fx,
                             float fy, int cx, int cy, void *stream);
 
+/* "Next" row f2: Projection_GPU::bilateralfilter (Projection_GPU.cu:213-246, launched :264-265) -- depth-only
+ * bilateral on the z of a packed float3 cloud, then x,y = normalized.x,y * z.  Race-free: in != out.
+ * Reference constants (Projection_GPU.cpp:3-5): radius 3, sigma_spatial 20, sigma_depth 100. */
+int kdme_depth_bilateral_xyz(const float *normalized_dev, const float *in_dev, float *out_dev, int width,
+                             int height, int window_radius, float sigma_spatial, float sigma_depth, void *stream);
+
+/* "Next" row f4: the evaluation metric of main.cpp:217-308 -- mean Euclidean distance (mm) between a
+ * method's cloud and the averaged ground-truth cloud over pixels whose z are both in (50, 15000).
+ * Packed float3 device clouds; synchronous (returns the mean and the pixel count on the host). */
+int kdme_mean_3d_error(const float *points_dev, const float *truth_dev, long long n_points, double *mean_out,
+                       long long *count_out, void *stream);
+
 /* ================= EdgeRefinedSuperpixel::depthmap_enhancement ============ */
 /* The guided cross-bilateral stage reached from TOFDepthInterpolation.cpp:65 ->
  * EdgeRefinedSuperpixel::EdgeRefining (EdgeRefinedSuperpixel.cu:208-223) ->

@@ -59,6 +59,8 @@ SIGNATURES = {
     "jbf_kernel_variant": (_i, [_vp]),
     "jbf_mrf": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _f, _f]),
     "kdme_projective_to_real": (_i, [_vp, _vp, _i, _i, _f, _f, _i, _i, _vp]),
+    "kdme_depth_bilateral_xyz": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "kdme_mean_3d_error": (_i, [_vp, _vp, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_longlong), _vp]),
     "kdme_guided_fill": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _i, _f, _f, _f, _vp]),
     "buf2d_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp]),
     "buf2d_destroy": (None, [_vp]),

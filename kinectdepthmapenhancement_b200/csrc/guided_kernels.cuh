@@ -197,4 +197,82 @@ mrf_kernel(const float* __restrict__ depth, const uint32_t* __restrict__ guide4,
     out[(long long)gy * width + gx] = (den == 0.0f) ? 0.0f : dp + num / den;
 }
 
+// Projection_GPU::bilateralfilter -- Projection_GPU.cu:213-246 (next row f2): depth-only bilateral on the
+// z of a packed float3 cloud, centred on the pixel's own z, weights expf(-dz^2/(2 sd^2)) * S; then
+// x,y = normalized.x,y * z.  Race-free (reads `in`, writes `out`).
+template <int TW, int TH>
+__global__ void __launch_bounds__(TW * TH)
+depth_bilateral_xyz_kernel(const float* __restrict__ normalized, const float* __restrict__ in,
+                           float* __restrict__ out, const float* __restrict__ ltab /*log2 S, [ws*ws]*/,
+                           int width, int height, int R, float nkd /* -log2e/(2 sd^2) */) {
+    constexpr int NT = TW * TH;
+    const int WS = 2 * R + 1, SP = TW + 2 * R, SH = TH + 2 * R;
+    extern __shared__ __align__(16) uint8_t smem_dbx[];
+    float* sZ = reinterpret_cast<float*>(smem_dbx);
+    float* sL = sZ + SP * SH;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = x0 - R + sx, gy = y0 - R + sy;
+        bool inb = (gx >= 0) & (gx < width) & (gy >= 0) & (gy < height);
+        sZ[idx] = inb ? __ldg(in + 3 * ((long long)gy * width + gx) + 2) : 0.f;
+    }
+    for (int idx = tid; idx < WS * WS; idx += NT) sL[idx] = __ldg(ltab + idx);
+    __syncthreads();
+    const int lx = tid % TW, ly = tid / TW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= width || gy >= height) return;
+    const float zc = sZ[(ly + R) * SP + lx + R];
+    float num = 0.f, den = 0.f;
+    for (int i = 0; i < WS; ++i) {
+        float rn = 0.f, rd = 0.f;
+        for (int j = 0; j < WS; ++j) {
+            const float zq = sZ[(ly + i) * SP + lx + j];
+            if (!(zq > kValidDepth)) continue;
+            const float e = zq - zc;
+            const float f = ex2_approx(fmaf(e * nkd, e, sL[i * WS + j] + kWeightBias));
+            rn = fmaf(f, e, rn);
+            rd += f;
+        }
+        num += rn;
+        den += rd;
+    }
+    const float z = (den == 0.0f) ? 0.0f : zc + num / den;
+    const long long k = (long long)gy * width + gx;
+    out[3 * k + 0] = __ldg(normalized + 3 * k + 0) * z;
+    out[3 * k + 1] = __ldg(normalized + 3 * k + 1) * z;
+    out[3 * k + 2] = z;
+}
+
+// main.cpp:217-308 (next row f4): sum of Euclidean distances between two packed float3 clouds over pixels
+// whose z are both in (50, 15000), and their count.  acc[0] += sum (double), acc[1] += count (as double).
+__global__ void __launch_bounds__(256) mean_3d_error_kernel(const float* __restrict__ pts,
+                                                            const float* __restrict__ truth, long long n,
+                                                            double* __restrict__ acc) {
+    double s = 0.0, c = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const float z = pts[3 * k + 2], zt = truth[3 * k + 2];
+        if (z > 50.0f && z < 15000.0f && zt > 50.0f && zt < 15000.0f) {
+            const float dz = z - zt, dy = pts[3 * k + 1] - truth[3 * k + 1], dx = pts[3 * k] - truth[3 * k];
+            s += (double)sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dz, dz), __fmul_rn(dy, dy)), __fmul_rn(dx, dx)));
+            c += 1.0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __shared__ double ss[8], sc[8];
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sc[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { s += ss[w]; c += sc[w]; }
+        atomicAdd(acc, s);
+        atomicAdd(acc + 1, c);
+    }
+}
+
 }  // namespace kdme

@@ -620,6 +620,56 @@ extern "C" int kdme_projective_to_real(const float* depth_dev, float* xyz_dev, i
     return KDME_OK;
 }
 
+// ------------------------------------------------------------------ next rows f2, f4
+extern "C" int kdme_depth_bilateral_xyz(const float* normalized_dev, const float* in_dev, float* out_dev, int width,
+                                        int height, int window_radius, float sigma_spatial, float sigma_depth,
+                                        void* stream) {
+    if (!normalized_dev || !in_dev || !out_dev) return fail(KDME_EINVAL, "kdme_depth_bilateral_xyz: NULL argument");
+    if (in_dev == out_dev) return fail(KDME_EINVAL, "kdme_depth_bilateral_xyz: in-place operation is not supported");
+    if (width <= 0 || height <= 0 || window_radius < 0 || window_radius > KDME_MAX_RADIUS || !(sigma_depth > 0))
+        return fail(KDME_EINVAL, "kdme_depth_bilateral_xyz: bad size, radius or sigma");
+    const int ws = 2 * window_radius + 1;
+    std::vector<float> lut;
+    host_spatial_lut(lut, ws, sigma_spatial);
+    std::vector<float> l2(lut.size());
+    for (size_t i = 0; i < lut.size(); i++) l2[i] = (lut[i] > 0.f) ? (float)std::log2((double)lut[i]) : -1.0e30f;
+    float* ltab = nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMallocAsync(&ltab, l2.size() * sizeof(float), st));
+    CK(cudaMemcpyAsync(ltab, l2.data(), l2.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // l2 is a stack-lifetime host buffer
+    constexpr int TW = 32, TH = 8;
+    const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
+    dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
+    depth_bilateral_xyz_kernel<TW, TH><<<grd, TW * TH, (size_t)(SP * SH + ws * ws) * 4, st>>>(
+        normalized_dev, in_dev, out_dev, ltab, width, height, window_radius,
+        (float)(-kLog2e / (2.0 * (double)sigma_depth * (double)sigma_depth)));
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(ltab, st));
+    return KDME_OK;
+}
+
+extern "C" int kdme_mean_3d_error(const float* points_dev, const float* truth_dev, long long n_points,
+                                  double* mean_out, long long* count_out, void* stream) {
+    if (!points_dev || !truth_dev || !mean_out || n_points <= 0)
+        return fail(KDME_EINVAL, "kdme_mean_3d_error: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* acc = nullptr;
+    CK(cudaMallocAsync(&acc, 2 * sizeof(double), st));
+    CK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+    long long blocks = (n_points + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    mean_3d_error_kernel<<<(int)blocks, 256, 0, st>>>(points_dev, truth_dev, n_points, acc);
+    CK(cudaGetLastError());
+    double host[2] = {0, 0};
+    CK(cudaMemcpyAsync(host, acc, sizeof(host), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFreeAsync(acc, st));
+    *mean_out = (host[1] > 0) ? host[0] / host[1] : 0.0;
+    if (count_out) *count_out = (long long)host[1];
+    return KDME_OK;
+}
+
 // ------------------------------------------------------------------ guided fill
 extern "C" int kdme_guided_fill(const float* depth_dev, const int32_t* labels_dev, const uint8_t* bgr_dev,
                                 size_t bgr_step, float* out_dev, int width, int height, int window_radius,

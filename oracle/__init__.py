@@ -79,6 +79,10 @@ def lib():
                                   C.c_int]
         L.orc_projective_to_real.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                              C.c_int, C.c_int]
+        L.orc_depth_bilateral_xyz.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_depth_bilateral_xyz_f64.argtypes = L.orc_depth_bilateral_xyz.argtypes
+        L.orc_mean_3d_error.argtypes = [_f32p, _f32p, C.c_int, C.POINTER(C.c_int)]
+        L.orc_mean_3d_error.restype = C.c_float
         _lib = L
     return _lib
 
@@ -103,6 +107,7 @@ def ref():
                      "ref_buf_get_weight", "ref_buf_update"):
             getattr(R, name).argtypes = [_f32p, _f32p, C.c_int, C.c_int]
         R.ref_buf_init.argtypes = [_f32p, C.c_int, C.c_int]
+        R.ref_depth_bilateral_xyz.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         _ref = R
     return _ref
 
@@ -246,6 +251,32 @@ def projective_to_real(depth, fx, fy, cx, cy):
     out = np.empty((h, w, 3), np.float32)
     lib().orc_projective_to_real(depth, out.reshape(-1), w, h, fx, fy, int(cx), int(cy))
     return out
+
+
+# Projection_GPU.cpp:3-5
+PROJ_WINDOW, PROJ_SIGMA_S, PROJ_SIGMA_D = 7, 20.0, 100.0
+
+
+def depth_bilateral_xyz(normalized, points, window=PROJ_WINDOW, sigma_s=PROJ_SIGMA_S, sigma_d=PROJ_SIGMA_D,
+                        threads=0, impl="oracle", precision="f32"):
+    """Projection_GPU::bilateralfilter (Projection_GPU.cu:213-246), race-free.  [H,W,3] float32 each."""
+    normalized, points = _f32(normalized), _f32(points)
+    h, w, _ = points.shape
+    lut = spatial_lut(window, sigma_s)   # same formula as Projection_GPU.cpp:35-43
+    out = np.empty_like(points)
+    threads = threads or n_cores()
+    fn = ref().ref_depth_bilateral_xyz if impl == "ref" else (
+        lib().orc_depth_bilateral_xyz_f64 if precision == "f64" else lib().orc_depth_bilateral_xyz)
+    fn(normalized.reshape(-1), points.reshape(-1), out.reshape(-1), lut, window, sigma_d, w, h, threads)
+    return out
+
+
+def mean_3d_error(points, truth):
+    """main.cpp:217-308: mean 3-D distance over pixels with both z in (50, 15000).  Returns (mean, count)."""
+    points, truth = _f32(points).reshape(-1), _f32(truth).reshape(-1)
+    cnt = C.c_int()
+    m = lib().orc_mean_3d_error(points, truth, points.size // 3, C.byref(cnt))
+    return float(m), cnt.value
 
 
 class Buffer2D:

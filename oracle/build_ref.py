@@ -31,6 +31,8 @@ RANGES = [
      "ef72d9fc489a674a458234e30bcd222afb6a302db3b79a5f3bba768619a0ae11"),
     ("MarkovRandomField/MarkovRandomField.cu", 3, 40,
      "032667abea302c33667fadb0ca847a440ba5be3d3def20cc23f1317f163d5182"),
+    ("Projection_GPU/Projection_GPU.cu", 213, 246,
+     "7b810ed18aa43e9fefe86819aba7e69e2ac89aacc452751ad09e2cf4b5f1e2ac"),
     ("ArrayBuffer/ArrayBuffer.cu", 9, 22,
      "221c6a62eede11af55778f4ffbd44ca08e4e75cc7a9f57a2a4c27b6cb889ee98"),
     ("ArrayBuffer/Buffer2D.cu", 13, 50,

@@ -18,7 +18,9 @@
  *   EdgeRefinedSuperpixel/EdgeRefinedSuperpixel.cpp:4-7,46-55 its constants and LUT
  *   ArrayBuffer/ArrayBuffer.cu:9-22, ArrayBuffer/Buffer2D.cu:13-140  device buffers
  *   MarkovRandomField/MarkovRandomField.cu:4-40               (next row f1)
+ *   Projection_GPU/Projection_GPU.cu:213-246                  (next row f2)
  *   DimensionConvertor/DimensionConvertor.h:34-75             (next row f3)
+ *   main.cpp:217-308                                          (next row f4, error metric)
  *
  * Parity pinning: the reference holds NO golden vectors, tests or fixtures for
  * this path.  The restatement is pinned instead against
@@ -590,5 +592,89 @@ ORC_API void orc_projective_to_real(const float *depth, float *xyz, int width, i
             xyz[3 * k + 0] = px;
             xyz[3 * k + 1] = py;
             xyz[3 * k + 2] = z;
+        }
+}
+
+/* f2: Projection_GPU.cu:213-246 -- depth-only bilateral on the z of a point cloud, centred on the
+ * pixel's own z (valid or not), weights expf(-dz^2/(2 sd^2)) * S (plain products, no skip guards),
+ * then x,y = normalized.x,y * z.  Race-free restatement: reads `in`, writes `out` (the reference
+ * overwrites optimized3d in place while neighbours read it).  xyz are packed float3. */
+ORC_API void orc_depth_bilateral_xyz(const float *normalized, const float *in, float *out, const float *spatial,
+                                     int window_size, float depth_sigma, int width, int height, int n_threads)
+{
+    int half = window_size / 2;
+    (void)n_threads;
+#pragma omp parallel for schedule(dynamic, 2) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            float num = 0.0f, den = 0.0f;
+            float zc = in[3 * (y * width + x) + 2];
+            for (int i = -half; i <= half; i++)
+                for (int j = -half; j <= half; j++) {
+                    int xj = x + j, yi = y + i;
+                    if (xj >= 0 && xj < width && yi >= 0 && yi < height && in[3 * (yi * width + xj) + 2] > 50.0f) {
+                        float zq = in[3 * (yi * width + xj) + 2];
+                        float dd = zq - zc;
+                        dd = dd * dd;
+                        float f = expf(-dd / (2.0f * (depth_sigma * depth_sigma)));
+                        f *= spatial[(i + half) * window_size + (j + half)];
+                        num += zq * f;
+                        den += f;
+                    }
+                }
+            float z = (den == 0.0f) ? 0.0f : num / den;
+            out[3 * (y * width + x) + 2] = z;
+            out[3 * (y * width + x) + 0] = normalized[3 * (y * width + x) + 0] * z;
+            out[3 * (y * width + x) + 1] = normalized[3 * (y * width + x) + 1] * z;
+        }
+}
+
+/* f4: main.cpp:217-308 -- mean Euclidean distance (mm) between a method's cloud and the averaged
+ * ground-truth cloud over pixels where both z are in (50, 15000); sequential float accumulation as
+ * the reference does (pow(float,2.0f) is the float overload; sqrtf). */
+ORC_API float orc_mean_3d_error(const float *pts, const float *truth, int n, int *count_out)
+{
+    float sum = 0.0f;
+    int count = 0;
+    for (int k = 0; k < n; k++) {
+        float z = pts[3 * k + 2], zt = truth[3 * k + 2];
+        if (z > 50.0f && z < 15000.0f && zt > 50.0f && zt < 15000.0f) {
+            float dz = z - zt, dy = pts[3 * k + 1] - truth[3 * k + 1], dx = pts[3 * k] - truth[3 * k];
+            sum += sqrtf(dz * dz + dy * dy + dx * dx);
+            count++;
+        }
+    }
+    if (count_out) *count_out = count;
+    return sum / (float)count;
+}
+
+/* fp64 evaluation of f2 (same formula; the only fp32 artefact kept is that expf() == 0 below -150 ln2). */
+ORC_API void orc_depth_bilateral_xyz_f64(const float *normalized, const float *in, float *out, const float *spatial,
+                                         int window_size, float depth_sigma, int width, int height, int n_threads)
+{
+    int half = window_size / 2;
+    double kd = 1.0 / (2.0 * (double)depth_sigma * (double)depth_sigma);
+    (void)n_threads;
+#pragma omp parallel for schedule(dynamic, 2) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            double num = 0.0, den = 0.0;
+            double zc = in[3 * (y * width + x) + 2];
+            for (int i = -half; i <= half; i++)
+                for (int j = -half; j <= half; j++) {
+                    int xj = x + j, yi = y + i;
+                    if (xj >= 0 && xj < width && yi >= 0 && yi < height && in[3 * (yi * width + xj) + 2] > 50.0f) {
+                        double zq = in[3 * (yi * width + xj) + 2];
+                        double a = (zq - zc) * (zq - zc) * kd;
+                        double f = (a <= ORC_EXP_ZERO_ARG) ? exp(-a) : 0.0;
+                        f *= (double)spatial[(i + half) * window_size + (j + half)];
+                        num += zq * f;
+                        den += f;
+                    }
+                }
+            float z = (den == 0.0) ? 0.0f : (float)(num / den);
+            out[3 * (y * width + x) + 2] = z;
+            out[3 * (y * width + x) + 0] = normalized[3 * (y * width + x) + 0] * z;
+            out[3 * (y * width + x) + 1] = normalized[3 * (y * width + x) + 1] * z;
         }
 }

@@ -72,6 +72,29 @@ REF_API void ref_mrf(int width, int height, float *depth, unsigned char *guide, 
     }
 }
 
+/* Projection_GPU.cu:264-265, race-free: each worker filters a private copy of the cloud and
+ * restores the element the kernel overwrote. */
+REF_API void ref_depth_bilateral_xyz(float *normalized, const float *in, float *out, float *spatial,
+                                     int window_size, float depth_sigma, int width, int height, int n_threads)
+{
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+    {
+        std::vector<float3> priv((const float3 *)in, (const float3 *)in + (size_t)width * height);
+#pragma omp for schedule(dynamic, 2)
+        for (int y = 0; y < height; y++) {
+            blockDim = {1, 1, 1}; threadIdx = {0, 0, 0};
+            for (int x = 0; x < width; x++) {
+                blockIdx = {x, y, 0};
+                size_t k = (size_t)y * width + x;
+                float3 saved = priv[k];
+                bilateralfilter((float3 *)normalized, priv.data(), spatial, window_size, depth_sigma, width, height);
+                ((float3 *)out)[k] = priv[k];
+                priv[k] = saved;
+            }
+        }
+    }
+}
+
 /* ArrayBuffer.cu:29, Buffer2D.cu:53-56,73-77,91-94,116-120,144-147 */
 #define REF_FOR_PIXELS                                   \
     blockDim = {1, 1, 1}; threadIdx = {0, 0, 0};         \

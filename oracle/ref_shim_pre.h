@@ -32,6 +32,7 @@ struct ref_dim3 { int x, y, z; };
 static thread_local ref_dim3 blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, threadIdx = {0, 0, 0};
 
 struct float2 { float x, y; };
+struct float3 { float x, y, z; };
 
 namespace cv { namespace gpu { struct GpuMat { unsigned char *data; }; } }
 

@@ -61,6 +61,15 @@ def main():
     xy = np.stack([d, d * 0.5], axis=-1).astype(np.float32)
     b2.insert_f32x2(xy)
     out["buf_xy_raw"] = b2.raw().copy()
+    # f2: Projection_GPU::bilateralfilter on the back-projected cloud
+    pts = oracle.projective_to_real(d, 525.0, 525.0, W // 2, H // 2)
+    z = np.where(pts[..., 2] > 0, pts[..., 2], 1)
+    norm = pts.copy()
+    norm[..., 0] /= z
+    norm[..., 1] /= z
+    out["f2_points"] = pts
+    out["f2_normalized"] = norm
+    out["f2_out"] = oracle.depth_bilateral_xyz(norm, pts, impl="ref", threads=1)
     np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **out)
     print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
 

@@ -42,6 +42,11 @@ def test_mrf_matches_reference_golden(gold):
     assert np.array_equal(out.view(np.uint32), gold["mrf_ws5"].view(np.uint32))
 
 
+def test_depth_bilateral_xyz_matches_reference_golden(gold):
+    out = oracle.depth_bilateral_xyz(gold["f2_normalized"], gold["f2_points"], threads=2)
+    assert np.array_equal(out.view(np.uint32), gold["f2_out"].view(np.uint32))
+
+
 def test_buffer2d_matches_reference_golden(gold):
     b = oracle.Buffer2D(96, 64)
     for f in gold["buf_frames"]:
