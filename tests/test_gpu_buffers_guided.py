@@ -107,3 +107,25 @@ def test_jbf_golden(golden_dir):
         out, _ = gpu_filter(gold["depth"], gold["guide"], r)
         assert np.array_equal(out > 0, gold[key] > 0)
         assert np.median(np.abs(out - gold[key])) <= 1e-3
+
+
+def test_guided_fill_full_size_properties():
+    """1920x1080 (config 3's guide size): holes stay holes only where no sample is in the window; values stay
+    inside the range of the window's samples; a constant depth is reproduced."""
+    from kinectdepthmapenhancement_b200 import guided_fill, synth
+    w, h, r = 1920, 1080, 3
+    d, c = synth.rgbd_frame(w, h, seed=6, frame=1, device="cuda")
+    out = guided_fill(d, c, None, r)
+    assert not torch.isnan(out).any()
+    valid = (d > 50).float()[None, None]
+    dil = torch.nn.functional.max_pool2d(valid, 2 * r + 1, 1, r)[0, 0] > 0
+    assert torch.equal(out > 0, dil)
+    big = torch.where(d > 50, d, torch.full_like(d, -1e30))[None, None]
+    small = torch.where(d > 50, d, torch.full_like(d, 1e30))[None, None]
+    mx = torch.nn.functional.max_pool2d(big, 2 * r + 1, 1, r)[0, 0]
+    mn = -torch.nn.functional.max_pool2d(-small, 2 * r + 1, 1, r)[0, 0]
+    m = out > 0
+    assert torch.all(out[m] <= mx[m] + 2e-3) and torch.all(out[m] >= mn[m] - 2e-3)
+    const = torch.where(d > 50, torch.full_like(d, 1500.25), torch.zeros_like(d))
+    oc = guided_fill(const, c, None, r)
+    assert torch.all((oc[oc > 0] - 1500.25).abs() <= 2.5e-4)

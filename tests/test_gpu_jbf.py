@@ -320,6 +320,31 @@ def test_upsample_matches_oracle_definition():
     check_against_f64(out, sparse, guide, 15, 70.0, 50.0, 20.0, "upsample 128x106 -> 480x270")
 
 
+def test_upsample_full_size_properties():
+    """Config 3 at full size (512x424 ToF depth -> 1920x1080 guide, r=7): every low-res sample lands on its
+    own site, the filled mask is the window dilation of the site mask, values stay inside the window range."""
+    from kinectdepthmapenhancement_b200 import synth
+    wl, hl, wh, hh, r = 512, 424, 1920, 1080, 7
+    lo, _ = synth.rgbd_frame(wl, hl, seed=6, frame=0, noise_rel=0.01, device="cuda", hole_frac=0.02)
+    _, hi = synth.rgbd_frame(wh, hh, seed=6, frame=0, device="cuda")
+    f = _jbf_cls()(wh, hh, window_radius=r)
+    out = f.Upsampling(lo, hi)
+    sparse = torch.from_numpy(oracle.scatter_lowres(lo.cpu().numpy(), wh, hh)).cuda()
+    valid = sparse > 50
+    assert int((sparse != 0).sum()) == int((lo != 0).sum())
+    assert torch.equal(out > 0, _dilate_gpu(valid, r))
+    big = torch.where(valid, sparse, torch.full_like(sparse, -1e30))[None, None]
+    small = torch.where(valid, sparse, torch.full_like(sparse, 1e30))[None, None]
+    mx = torch.nn.functional.max_pool2d(big, 2 * r + 1, 1, r)[0, 0]
+    mn = -torch.nn.functional.max_pool2d(-small, 2 * r + 1, 1, r)[0, 0]
+    m = out > 0
+    assert torch.all(out[m] <= mx[m] + 2e-3) and torch.all(out[m] >= mn[m] - 2e-3)
+    # and the dense path on the materialised sparse image gives the same result bit for bit
+    g4 = f.presmooth(hi[None])
+    dense = f.filter_guide4(sparse[None].contiguous(), g4)[0]
+    assert torch.equal(dense.view(torch.int32), out.view(torch.int32))
+
+
 def test_mrf_and_projective_to_real():
     from kinectdepthmapenhancement_b200 import projective_to_real
     depth, bgr = synth_np(160, 120, seed=12, frame=0)

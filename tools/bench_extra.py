@@ -5,6 +5,7 @@
   python tools/bench_extra.py buffer2d   # Buffer2D kernels vs the HBM roofline
   python tools/bench_extra.py upsample   # configs[2]: 512x424 ToF depth -> 1920x1080 guide
   python tools/bench_extra.py single     # one 640x480 frame per call (latency of Process)
+  python tools/bench_extra.py guided     # guided cross-bilateral fill at 1920x1080
   torchrun ... tools/bench_extra.py band # configs[4]: 16384x16384 r=9 row bands + NVLink halo exchange
 
 Each prints one JSON object; copies are kept under profiles/.
@@ -113,6 +114,19 @@ def upsample():
                       "hbm_gbs_algorithmic": byt / ms / 1e6, "filled_fraction": float((out > 0).float().mean())}))
 
 
+def guided():
+    from kinectdepthmapenhancement_b200 import guided_fill
+    w, h = 1920, 1080
+    d, c = synth.rgbd_frame(w, h, seed=6, frame=1, device="cuda")
+    lab = ((torch.arange(h, device="cuda")[:, None] // 40) * 64 + (torch.arange(w, device="cuda")[None, :] // 40)).int().contiguous()
+    out = torch.empty_like(d)
+    ms_l = ev_time(lambda: guided_fill(d, c, lab, 3, out=out), 20)
+    ms_n = ev_time(lambda: guided_fill(d, c, None, 3, out=out), 20)
+    print(json.dumps({"workload": "guided cross-bilateral fill (depthmap_enhancement) 1920x1080, window 7, sigmas 30/50/70",
+                      "ms_with_labels": ms_l, "ms_no_labels": ms_n, "mpixel_s_with_labels": w * h / ms_l / 1e3,
+                      "algorithmic_bytes": w * h * (4 + 3 + 4 + 4), "hbm_gbs_algorithmic": w * h * 15 / ms_l / 1e6}))
+
+
 def single():
     w, h, r = 640, 480, 7
     d, c = synth.rgbd_frame(w, h, seed=1, frame=0, device="cuda")
@@ -184,4 +198,4 @@ def band():
 
 
 if __name__ == "__main__":
-    {"sweep": sweep, "buffer2d": buffer2d, "upsample": upsample, "single": single, "band": band}[sys.argv[1]]()
+    {"sweep": sweep, "buffer2d": buffer2d, "upsample": upsample, "single": single, "band": band, "guided": guided}[sys.argv[1]]()
