@@ -45,6 +45,7 @@ struct JbfParams {
     long long guide_frame_stride;   // words
     int guide_pitch;                // words per row
     const float* ltab;           // [(2r+1)][LP]: log2(S_ij)+bias, or bias where S_ij == 0
+    const float* ltab_pairs;     // [(2r+1)][LPP][2]: {L[i][j], L[i][j-1]} for j = 1..2r (packed-math kernel)
     float nkc;                   // -log2e / (2 sigma_c^2)
     float sq, inv_sq;            // depth scale sqrt(log2e/(2 sigma_d^2)) and inverse
     float e_thr;                 // sqrt(150): scaled |d - m| beyond which fp32 expf() == 0
@@ -69,7 +70,8 @@ struct JbfTile {
     static constexpr int NW = 2 * RP + 4;          // words fetched per row per thread
     static constexpr int C0 = RP - R;              // first used column of the fetched segment
     static constexpr int PLANE = ((SP * SH * 4 + 127) / 128) * 128;
-    static constexpr int LBYTES = ((WS * LP * 4 + 127) / 128) * 128;
+    static constexpr int LPP = (WS - 1 + 1) & ~1;  // pairs per LUT row, padded to an even count (16-byte rows)
+    static constexpr int LBYTES = ((WS * (LPP > LP / 2 ? LPP * 2 : LP) * 4 + 127) / 128) * 128;
     static constexpr int SMEM = 3 * PLANE + LBYTES + 128;
 };
 
@@ -82,12 +84,13 @@ __device__ __forceinline__ int upsample_site(int x, int W, int wl) {
     return ((int)(((2LL * xl + 1) * W) / (2LL * wl)) == x) ? xl : -1;
 }
 
-template <int R, int TW, int TH, int MINB>
+template <int R, int TW, int TH, int MINB, bool PACKED>
 __global__ void __launch_bounds__((TW / 4) * TH, MINB)
 jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_constant__ CUtensorMap tm_guide,
                 const JbfParams p) {
     using T = JbfTile<R, TW, TH>;
     constexpr int WS = T::WS, RP = T::RP, SP = T::SP, SH = T::SH, LP = T::LP, NT = T::NT, NW = T::NW, C0 = T::C0;
+    constexpr int LPP = T::LPP;
 
     extern __shared__ __align__(128) uint8_t smem_fast[];
     float* sD = reinterpret_cast<float*>(smem_fast);
@@ -137,7 +140,11 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         }
     }
     // spatial LUT rows (log2 domain, bias folded in)
-    for (int idx = tid; idx < WS * LP; idx += NT) sL[idx] = __ldg(p.ltab + idx);
+    if (PACKED) {
+        for (int idx = tid; idx < WS * LPP * 2; idx += NT) sL[idx] = __ldg(p.ltab_pairs + idx);
+    } else {
+        for (int idx = tid; idx < WS * LP; idx += NT) sL[idx] = __ldg(p.ltab + idx);
+    }
     if (p.mode == kStageTma) mbar_wait(bar, 0);
     __syncthreads();
 
@@ -190,6 +197,10 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         }
     }
     const float nkc = p.nkc;
+    float delta[4], num[4], den[4];
+    bool any[4];
+
+    if constexpr (!PACKED) {
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -235,8 +246,6 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     // pass-1 weighted mean, in scaled tile-relative units
     // the mean is kept as (d0, delta): e = (d - d0) - delta keeps full precision even when the tile
     // spans metres of depth
-    float delta[4];
-    bool any[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         any[k] = wsum[k] > 0.f;
@@ -244,7 +253,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     }
 
     const float e_thr = p.e_thr;
-    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4; ++k) { num[k] = 0.f; den[k] = 0.f; }
 #pragma unroll 1
     for (int i = 0; i < WS; ++i) {
         const int rowoff = (ly + i) * SP + colbase;
@@ -286,6 +295,154 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) { num[k] += rnum[k]; den[k] += rden[k]; }
+    }
+
+    } else {
+        // ---- packed-math form: pixels (0,1) and (2,3) of the thread share one tap column, so the FADD/FFMA
+        // of two taps issue as one FADD2/FFMA2 (scalar operands broadcast, LUT entries pre-paired as
+        // {L[j], L[j-1]}).  Per tap PAIR: 2 VABSDIFF4 + 2 IDP.4A + FADD2 + FFMA2 + 2 MUFU.EX2 + FFMA2 + FADD2
+        // (pass 1), plus FADD2 + 2 FSETP + 2 predicated FFMA (pass 2).  Same arithmetic per lane as above.
+        const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+        const f32x2 nkc2 = pack2(nkc, nkc);
+        f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull};
+#pragma unroll 1
+        for (int i = 0; i < WS; ++i) {
+            const int rowoff = (ly + i) * SP + colbase;
+            uint32_t gq[NW], mq[NW];
+            float dq[NW];
+            f32x2 LPr[LPP];
+#pragma unroll
+            for (int v = 0; v < NW / 4; ++v) {
+                const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
+                const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
+                const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
+                gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
+                dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
+                mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
+            }
+#pragma unroll
+            for (int v = 0; v < LPP / 2; ++v) {
+                const float4 l4 = *reinterpret_cast<const float4*>(sL + (i * LPP + 2 * v) * 2);
+                LPr[2 * v] = pack2(l4.x, l4.y);
+                LPr[2 * v + 1] = pack2(l4.z, l4.w);
+            }
+            f32x2 raccP[2] = {0ull, 0ull}, rwsP[2] = {0ull, 0ull};
+#pragma unroll
+            for (int c = C0; c < C0 + WS + 3; ++c) {
+                const float dsh = dq[c] - d0;
+                const f32x2 dsh2 = pack2(dsh, dsh);
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int j0 = c - C0 - 2 * pr;   // tap column index of the pair's first pixel; second uses j0-1
+                    const bool v0 = (j0 >= 0 && j0 < WS), v1 = (j0 - 1 >= 0 && j0 - 1 < WS);
+                    if (v0 && v1) {
+                        const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq[c]), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq[c]);
+                        const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, mq[c])),
+                                               __uint_as_float(__dp4a(ad1, ad1, mq[c])));
+                        const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, LPr[j0 - 1]);
+                        float a0, a1;
+                        unpack2(ar, a0, a1);
+                        const f32x2 ff = pack2(ex2_approx(a0), ex2_approx(a1));
+                        raccP[pr] = fma2(ff, dsh2, raccP[pr]);
+                        rwsP[pr] = add2(rwsP[pr], ff);
+                    } else if (v0 || v1) {   // window edge: only one pixel of the pair sees this column
+                        const int k = v0 ? 2 * pr : 2 * pr + 1;
+                        const int j = v0 ? j0 : j0 - 1;
+                        float l_lo, l_hi;
+                        unpack2(LPr[(j == 0) ? 0 : j - 1], l_lo, l_hi);   // L[0] = pair 0 hi, L[j] = pair j-1 lo
+                        const float lj = (j == 0) ? l_hi : l_lo;
+                        const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
+                        const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
+                        const float f = ex2_approx(fmaf(cdf, nkc, lj));
+                        const f32x2 ff = v0 ? pack2(f, 0.f) : pack2(0.f, f);
+                        raccP[pr] = fma2(ff, dsh2, raccP[pr]);
+                        rwsP[pr] = add2(rwsP[pr], ff);
+                    }
+                }
+            }
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) { accP[pr] = add2(accP[pr], raccP[pr]); wsP[pr] = add2(wsP[pr], rwsP[pr]); }
+        }
+        float acc[4], wsum[4];
+        unpack2(accP[0], acc[0], acc[1]); unpack2(accP[1], acc[2], acc[3]);
+        unpack2(wsP[0], wsum[0], wsum[1]); unpack2(wsP[1], wsum[2], wsum[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            any[k] = wsum[k] > 0.f;
+            delta[k] = any[k] ? (acc[k] / wsum[k]) : 0.f;
+        }
+        const f32x2 ndelP[2] = {pack2(-delta[0], -delta[1]), pack2(-delta[2], -delta[3])};
+        const float e_thr = p.e_thr;
+        f32x2 numP[2] = {0ull, 0ull}, denP[2] = {0ull, 0ull};
+#pragma unroll 1
+        for (int i = 0; i < WS; ++i) {
+            const int rowoff = (ly + i) * SP + colbase;
+            uint32_t gq[NW], mq[NW];
+            float dq[NW];
+            f32x2 LPr[LPP];
+#pragma unroll
+            for (int v = 0; v < NW / 4; ++v) {
+                const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
+                const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
+                const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
+                gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
+                dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
+                mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
+            }
+#pragma unroll
+            for (int v = 0; v < LPP / 2; ++v) {
+                const float4 l4 = *reinterpret_cast<const float4*>(sL + (i * LPP + 2 * v) * 2);
+                LPr[2 * v] = pack2(l4.x, l4.y);
+                LPr[2 * v + 1] = pack2(l4.z, l4.w);
+            }
+            f32x2 rnumP[2] = {0ull, 0ull}, rdenP[2] = {0ull, 0ull};
+#pragma unroll
+            for (int c = C0; c < C0 + WS + 3; ++c) {
+                const float dsh = dq[c] - d0;
+                const f32x2 dsh2 = pack2(dsh, dsh);
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int j0 = c - C0 - 2 * pr;
+                    const bool v0 = (j0 >= 0 && j0 < WS), v1 = (j0 - 1 >= 0 && j0 - 1 < WS);
+                    if (v0 && v1) {
+                        const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq[c]), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq[c]);
+                        const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, mq[c])),
+                                               __uint_as_float(__dp4a(ad1, ad1, mq[c])));
+                        const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, LPr[j0 - 1]);
+                        const f32x2 ee = add2(dsh2, ndelP[pr]);
+                        float a0, a1, e0, e1;
+                        unpack2(ar, a0, a1);
+                        unpack2(ee, e0, e1);
+                        // fp32 expf(-(d-m)^2/(2 sd^2)) == 0  <=>  factor skipped (.cu:67-68)
+                        if (!(fabsf(e0) > e_thr)) a0 = fmaf(-e0, e0, a0);
+                        if (!(fabsf(e1) > e_thr)) a1 = fmaf(-e1, e1, a1);
+                        const f32x2 ff = pack2(ex2_approx(a0), ex2_approx(a1));
+                        rnumP[pr] = fma2(ff, ee, rnumP[pr]);
+                        rdenP[pr] = add2(rdenP[pr], ff);
+                    } else if (v0 || v1) {
+                        const int k = v0 ? 2 * pr : 2 * pr + 1;
+                        const int j = v0 ? j0 : j0 - 1;
+                        float l_lo, l_hi;
+                        unpack2(LPr[(j == 0) ? 0 : j - 1], l_lo, l_hi);
+                        const float lj = (j == 0) ? l_hi : l_lo;
+                        const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
+                        const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
+                        float arg = fmaf(cdf, nkc, lj);
+                        const float e = dsh - delta[k];
+                        if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
+                        const float f = ex2_approx(arg);
+                        const f32x2 ff = v0 ? pack2(f, 0.f) : pack2(0.f, f);
+                        const f32x2 ee = v0 ? pack2(e, 0.f) : pack2(0.f, e);
+                        rnumP[pr] = fma2(ff, ee, rnumP[pr]);
+                        rdenP[pr] = add2(rdenP[pr], ff);
+                    }
+                }
+            }
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) { numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
+        }
+        unpack2(numP[0], num[0], num[1]); unpack2(numP[1], num[2], num[3]);
+        unpack2(denP[0], den[0], den[1]); unpack2(denP[1], den[2], den[3]);
     }
 
     // ---------------- epilogue: back to millimetres, 16-byte store

@@ -98,12 +98,13 @@ struct jbf_handle {
     int guide_pitch = 0;             // words
     uint8_t* smooth_bgr = nullptr;   // packed copy for getSmoothImage_Device (lazy)
     float* ltab_dev = nullptr;       // fast layout [WS][LP]
+    float* ltab_pairs_dev = nullptr; // packed-math layout [WS][LPP][2] = {L[i][j], L[i][j-1]}, j = 1..WS-1
     float* ltab_generic_dev = nullptr;  // [WS][WS]
     // derived
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
-    bool force_no_tma = false, force_big_tiles = false;
+    bool force_no_tma = false, force_big_tiles = false, scalar_math = false;
     int last_variant = 0;
     // host pipeline (jbf_process_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -142,6 +143,16 @@ static int build_tables(jbf_handle* h) {
             lf[(size_t)i * lp + j] = l;
             lg[(size_t)i * ws + j] = l;
         }
+    const int lpp = (ws - 1 + 1) & ~1;
+    std::vector<float> lpairs((size_t)ws * (lpp > 0 ? lpp : 1) * 2, 0.f);
+    for (int i = 0; i < ws; i++)
+        for (int j = 1; j < ws; j++) {
+            lpairs[((size_t)i * lpp + (j - 1)) * 2 + 0] = lf[(size_t)i * lp + j];
+            lpairs[((size_t)i * lpp + (j - 1)) * 2 + 1] = lf[(size_t)i * lp + j - 1];
+        }
+    CK(cudaMalloc(&h->ltab_pairs_dev, lpairs.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->ltab_pairs_dev, lpairs.data(), lpairs.size() * sizeof(float), cudaMemcpyHostToDevice,
+                       h->stream));
     CK(cudaMalloc(&h->ltab_dev, lf.size() * sizeof(float)));
     CK(cudaMalloc(&h->ltab_generic_dev, lg.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->ltab_dev, lf.data(), lf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -183,6 +194,7 @@ static int build_tables(jbf_handle* h) {
     if (getenv("KDME_FORCE_GENERIC")) h->fast = false;
     h->force_no_tma = getenv("KDME_NO_TMA") != nullptr;
     h->force_big_tiles = getenv("KDME_BIG_TILES") != nullptr;
+    h->scalar_math = getenv("KDME_SCALAR_MATH") != nullptr;
     return KDME_OK;
 }
 
@@ -252,6 +264,7 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->guide4);
     cudaFree(h->smooth_bgr);
     cudaFree(h->ltab_dev);
+    cudaFree(h->ltab_pairs_dev);
     cudaFree(h->ltab_generic_dev);
     cudaFree(h->ps_space_dev);
     cudaFree(h->ps_color_dev);
@@ -309,12 +322,12 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
 }
 
 // One (radius, tile height) instantiation: encode the TMA maps for its box and launch.
-template <int R, int TH>
+template <int R, int TH, bool PACKED>
 static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
     constexpr int TW = 64;
     constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : 4;
     using T = JbfTile<R, TW, TH>;
-    auto kern = jbf_fast_kernel<R, TW, TH, MINB>;
+    auto kern = jbf_fast_kernel<R, TW, TH, MINB, PACKED>;
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
@@ -329,7 +342,7 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
                              (long long)p.guide_pitch * 4, (long long)p.guide_pitch * rows * 4, T::SP, T::SH);
         if (ok) p.mode = kStageTma;
     }
-    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0);
+    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (PACKED ? 0x400 : 0);
     dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
     kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
     CK(cudaGetLastError());
@@ -364,6 +377,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
     if (h->fast) {
         p.ltab = h->ltab_dev;
+        p.ltab_pairs = h->ltab_pairs_dev;
         const bool want_tma = p.mode == kStagePlain && !h->force_no_tma && (h->width % 4 == 0) &&
                               (guide_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
                               ((reinterpret_cast<uintptr_t>(guide4) & 15) == 0);
@@ -374,7 +388,8 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
         const long long ctas16 = (long long)((h->width + 63) / 64) * ((out_rows + 15) / 16) * n;
         const bool small_tiles = (ctas16 < 4LL * 148 * 3) && (rows == out_rows) && !h->force_big_tiles;
         switch (h->radius) {
-#define X(R) case R: return small_tiles ? launch_fast_rt<R, 8>(h, p, want_tma, rows) : launch_fast_rt<R, 16>(h, p, want_tma, rows);
+#define X(R) case R: return h->scalar_math ? (small_tiles ? launch_fast_rt<R, 8, false>(h, p, want_tma, rows) : launch_fast_rt<R, 16, false>(h, p, want_tma, rows)) \
+                                           : (small_tiles ? launch_fast_rt<R, 8, true>(h, p, want_tma, rows) : launch_fast_rt<R, 16, true>(h, p, want_tma, rows));
             KDME_FAST_RADII(X)
 #undef X
         }
@@ -384,6 +399,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     JbfGenericParams gp;
     gp.base = p;
     gp.base.ltab = h->ltab_generic_dev;
+    gp.base.ltab_pairs = nullptr;
     gp.radius = h->radius; gp.cd_skip = h->cd_skip; gp.use_color = h->use_color; gp.use_depth = h->use_depth;
     constexpr int TW = 32, TH = 8;
     const int SP = TW + 2 * h->radius, SH = TH + 2 * h->radius, ws = 2 * h->radius + 1;
@@ -586,7 +602,7 @@ extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
     return h->smooth_bgr;
 }
 
-extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x300)) : -1; }
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x700)) : -1; }
 
 // ------------------------------------------------------------------ MRF (next row f1)
 extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,

@@ -10,6 +10,15 @@
 #define ITERS 2048
 #define NCH 8
 
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+
 template <int OP>
 __global__ void __launch_bounds__(256) pipe_kernel(float* out, float a, float b, uint32_t ua, int iters) {
     __shared__ float lut[256];   // per-channel colour-range LUT (OP 7): exp(-k^2/(2 sigma_c^2))
@@ -38,6 +47,28 @@ __global__ void __launch_bounds__(256) pipe_kernel(float* out, float a, float b,
                     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(fmaf(cdf, a, b)));
                     x[i] = fmaf(f, b, x[i]);
                     x[(i + 1) % NCH] += f;
+                }
+                if (OP == 8) {  // packed fp32x2 FMA (Blackwell FFMA2): counts as ONE instruction, two FMAs
+                    unsigned long long v = pack2(x[i], x[(i + 4) % NCH]);
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(pack2(a, a)), "l"(pack2(b, b)));
+                    unpack2(v, x[i], x[(i + 4) % NCH]);
+                }
+                if (OP == 9 && (i & 1) == 0) {  // pass-1 body for TWO taps with FADD2/FFMA2 (one count = two taps)
+                    uint32_t ad0 = __vabsdiffu4(u[i], ua + it * 4 + rep), ad1 = __vabsdiffu4(u[i + 1], ua + it * 4 + rep);
+                    unsigned long long xx = pack2(__uint_as_float(__dp4a(ad0, ad0, 0x4B000000u)),
+                                                  __uint_as_float(__dp4a(ad1, ad1, 0x4B000000u)));
+                    unsigned long long cd, ar;
+                    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(cd) : "l"(xx), "l"(pack2(-8388608.0f, -8388608.0f)));
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ar) : "l"(cd), "l"(pack2(a, a)), "l"(pack2(b, b)));
+                    float a0, a1, f0, f1;
+                    unpack2(ar, a0, a1);
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(f0) : "f"(a0));
+                    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(f1) : "f"(a1));
+                    unsigned long long ff = pack2(f0, f1), acc = pack2(x[i], x[i + 1]), ws = pack2(x[(i + 2) % NCH], x[(i + 3) % NCH]);
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ff), "l"(pack2(b, b)));
+                    asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(ws) : "l"(ff));
+                    unpack2(acc, x[i], x[i + 1]);
+                    unpack2(ws, x[(i + 2) % NCH], x[(i + 3) % NCH]);
                 }
                 if (OP == 7) {  // pass-1 tap body with per-channel colour LUTs instead of IDP.4A + MUFU
                     uint32_t ad = __vabsdiffu4(u[i], ua + it * 4 + rep);
@@ -112,7 +143,8 @@ int main() {
     int clk_khz = 0;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     double ffma = run<0>(sms, 8, 1), fadd = run<1>(sms, 8, 1), mufu = run<2>(sms, 8, 1), vabs = run<3>(sms, 8, 1),
-           idp = run<4>(sms, 8, 1), tap1 = run<5>(sms, 8, 1), tap2 = run<6>(sms, 8, 1), tap1lut = run<7>(sms, 8, 1);
+           idp = run<4>(sms, 8, 1), tap1 = run<5>(sms, 8, 1), tap2 = run<6>(sms, 8, 1), tap1lut = run<7>(sms, 8, 1),
+           ffma2 = run<8>(sms, 8, 1), tap1x2 = run<9>(sms, 8, 1);
     // LDS.128
     float* d; cudaMalloc(&d, 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -126,11 +158,11 @@ int main() {
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_max_mhz\": %.0f, "
            "\"ffma_tflops\": %.2f, \"ffma_ginst_s\": %.1f, \"fadd_ginst_s\": %.1f, \"mufu_ex2_ginst_s\": %.1f, "
            "\"vabsdiff4_ginst_s\": %.1f, \"idp4a_ginst_s\": %.1f, \"tap_pass1_gtaps_s\": %.1f, \"tap_pass2_gtaps_s\": %.1f, "
-           "\"tap_pass1_channel_lut_gtaps_s\": %.1f, \"lds128_tb_s\": %.2f, "
+           "\"tap_pass1_channel_lut_gtaps_s\": %.1f, \"ffma2_ginst_s\": %.1f, \"tap_pass1_f32x2_gtaps_s\": %.1f, \"lds128_tb_s\": %.2f, "
            "\"ffma_per_clk_per_sm\": %.1f, \"mufu_per_clk_per_sm\": %.1f, \"vabsdiff4_per_clk_per_sm\": %.1f, "
            "\"idp4a_per_clk_per_sm\": %.1f, \"how\": \"8 CTAs x 256 thr per SM, 8 independent chains, best of 5, per-clk at max clock\"}\n",
            p.name, sms, clk_khz / 1e3, 2 * ffma / 1e12, ffma / 1e9, fadd / 1e9, mufu / 1e9, vabs / 1e9, idp / 1e9,
-           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, lds_bytes / 1e12, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
+           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, ffma2 / 1e9, tap1x2 / 1e9, lds_bytes / 1e12, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
            vabs / (sms * clk_khz * 1e3), idp / (sms * clk_khz * 1e3));
     return 0;
 }
