@@ -119,6 +119,22 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     } else {
         const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
         const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
+        // upsample: the low-res sample (if any) of every staged column and row, computed once per tile
+        // (sM is free until stage B: its first SP + SH words hold the two maps)
+        int* colmap = reinterpret_cast<int*>(sM);
+        int* rowmap = colmap + SP;
+        if (p.mode == kStageUpsample) {
+            for (int t = tid; t < SP + SH; t += NT) {
+                if (t < SP) {
+                    const int gx = sx0 + t;
+                    colmap[t] = (gx >= 0 && gx < p.width) ? upsample_site(gx, p.width, p.wl) : -1;
+                } else {
+                    const int gy = sy0 + (t - SP);
+                    rowmap[t - SP] = (gy >= 0 && gy < p.height) ? upsample_site(gy, p.height, p.hl) : -1;
+                }
+            }
+            __syncthreads();
+        }
         for (int idx = tid; idx < SP * SH; idx += NT) {
             int sy = idx / SP, sx = idx - sy * SP;
             int gx = sx0 + sx, gy = sy0 + sy;
@@ -129,9 +145,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 g = __ldg(gsrc + (long long)gy * p.guide_pitch + gx);
                 if (p.mode == kStagePlain) {
                     d = __ldg(dsrc + (long long)gy * p.width + gx);
-                } else {  // upsample: scatter the low-res sample onto its high-res site
-                    int xl = upsample_site(gx, p.width, p.wl);
-                    int yl = upsample_site(gy, p.height, p.hl);
+                } else {  // scatter the low-res sample onto its high-res site
+                    const int xl = colmap[sx], yl = rowmap[sy];
                     if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
                 }
             }

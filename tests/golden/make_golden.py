@@ -9,9 +9,10 @@ The reference itself ships no golden vectors; these fixtur
 committed C restatement (oracle/kdme_oracle.c) to the reference on machines where
 /root/reference is absent (the GPU box).
 
-color.jpg is the reference's bundled sample frame input/color.jpg (sha256 11b7776a...589cd),
-copied byte-for-byte as a data fixture; the matching input/depth.xml is a stripped large blob
-(.MISSING_LARGE_BLOBS) and is replaced by a seeded surrogate depth everywhere.
+guide_frame_640x480.png holds the decoded pixels (cv2.imread(..., 1); pixel sha256 67e5a97a...1614c) of
+the reference's bundled sample frame input/color.jpg, written losslessly by this script; the matching
+input/depth.xml is a stripped large blob (.MISSING_LARGE_BLOBS) and is replaced by a seeded surrogate
+depth everywhere.
 """
 import os
 import sys
@@ -70,6 +71,10 @@ def main():
     out["f2_points"] = pts
     out["f2_normalized"] = norm
     out["f2_out"] = oracle.depth_bilateral_xyz(norm, pts, impl="ref", threads=1)
+    import cv2
+    src = os.path.join(build_ref.REF, "input", "color.jpg")
+    if os.path.isfile(src):
+        cv2.imwrite(os.path.join(HERE, "guide_frame_640x480.png"), cv2.imread(src, 1), [cv2.IMWRITE_PNG_COMPRESSION, 9])
     np.savez_compressed(os.path.join(HERE, "ref_golden.npz"), **out)
     print("wrote ref_golden.npz:", {k: v.shape for k, v in out.items()})
 

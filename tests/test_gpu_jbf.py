@@ -174,7 +174,7 @@ def test_holes_threshold_and_all_holes():
 
 def test_presmooth_bit_exact_vs_oracle(golden_dir):
     import cv2
-    img = cv2.imread(os.path.join(golden_dir, "color.jpg"), 1)
+    img = cv2.imread(os.path.join(golden_dir, "guide_frame_640x480.png"), 1)
     h, w, _ = img.shape
     f = _jbf_cls()(w, h)
     g4 = f.presmooth(torch.from_numpy(img[None]).cuda())[0].cpu().numpy().view(np.uint32)
@@ -196,7 +196,7 @@ def test_process_on_bundled_frame_reference_defaults(golden_dir):
     5/30/30).  input/depth.xml is a stripped blob in the reference checkout; a seeded surrogate depth
     is used and reported as such."""
     import cv2
-    img = cv2.imread(os.path.join(golden_dir, "color.jpg"), 1)
+    img = cv2.imread(os.path.join(golden_dir, "guide_frame_640x480.png"), 1)
     depth, _ = synth_np(640, 480, seed=2013, frame=0)
     JBF = _jbf_cls()
     f = JBF(640, 480)

@@ -159,7 +159,7 @@ def test_skip_if_zero_depth_guard():
 
 def test_presmooth_matches_opencv_definition(golden_dir):
     cv2 = pytest.importorskip("cv2")
-    img = cv2.imread(os.path.join(golden_dir, "color.jpg"), 1)
+    img = cv2.imread(os.path.join(golden_dir, "guide_frame_640x480.png"), 1)
     assert img is not None and img.shape == (480, 640, 3)
     ours = oracle.presmooth(img)
     theirs = cv2.bilateralFilter(img, 5, 30, 30)
