@@ -41,3 +41,38 @@ def test_reference_call_sites_compile_and_link():
                         "-L", libdir, "-lkdme_b200", "-Wl,-rpath," + libdir], check=True)
         res = subprocess.run([exe], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def _build_example(tmpdir):
+    from kinectdepthmapenhancement_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = os.path.join(tmpdir, "jbf_main")
+    subprocess.run(["g++", "-std=c++11", "-DKDME_NO_OPENCV", "-I", os.path.join(ROOT, "include"),
+                    "-I", "/usr/local/cuda/include", os.path.join(ROOT, "examples", "jbf_main.cpp"), "-o", exe,
+                    "-L", libdir, "-lkdme_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir],
+                   check=True)
+    return exe
+
+
+def test_cpp_example_builds_and_degrades_cleanly_without_gpu():
+    import torch
+    with tempfile.TemporaryDirectory() as td:
+        exe = _build_example(td)
+        res = subprocess.run([exe], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        if not torch.cuda.is_available():
+            assert "no CUDA device" in res.stdout
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_cpp_example_runs_on_gpu():
+    """Pure C++ caller over the C ABI: the reference's call sequence fills every isolated hole."""
+    with tempfile.TemporaryDirectory() as td:
+        exe = _build_example(td)
+        for r in ("2", "7"):
+            res = subprocess.run([exe, r], capture_output=True, text=True)
+            assert res.returncode == 0, res.stdout + res.stderr
+            assert "holes" in res.stdout and "-> 0" in res.stdout
