@@ -246,6 +246,25 @@ def test_process_host_pipeline_matches_device_path():
     assert torch.equal(oh, want)
 
 
+def test_pitched_gpumat_step_is_honoured():
+    """cv::gpu::GpuMat rows may be padded (step > 3*width); the reference ignores step (it indexes
+    (y*W+x)*3, JointBilateralFilter.cu:22-24) and only works for continuous images.  Through the C ABI a
+    pitched image gives the same result as its continuous copy."""
+    import ctypes as C
+    from kinectdepthmapenhancement_b200 import _lib, synth
+    w, h, pad = 160, 120, 7
+    depth, bgr = synth.rgbd_frame(w, h, seed=9, frame=0, device="cuda")
+    pitched = torch.zeros((h, w + pad, 3), dtype=torch.uint8, device="cuda")
+    pitched[:, :w] = bgr
+    f = _jbf_cls()(w, h, window_radius=3)
+    f.Process(depth, bgr)
+    want = f.getFiltered_Device().clone()
+    _lib.check(_lib.lib().jbf_process(f._h, depth.data_ptr(), pitched.data_ptr(), 3 * (w + pad)))
+    assert torch.equal(f.getFiltered_Device(), want)
+    rc = _lib.lib().jbf_process(f._h, depth.data_ptr(), pitched.data_ptr(), 3 * w - 1)
+    assert rc == _lib.KDME_EINVAL
+
+
 def test_argument_errors():
     from kinectdepthmapenhancement_b200 import KdmeError
     JBF = _jbf_cls()
