@@ -387,10 +387,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
         // y_off/out_rows and always use 64x16.
         const long long ctas16 = (long long)((h->width + 63) / 64) * ((out_rows + 15) / 16) * n;
         const bool small_tiles = (ctas16 < 4LL * 148 * 3) && (rows == out_rows) && !h->force_big_tiles;
-        // one Kinect frame (300 tiles of 64x16): 32x8 tiles = 1200 CTAs, ~8 per SM, for an even load
-        const bool tiny_tiles = small_tiles && (ctas16 < 3LL * 148) && !h->scalar_math;
-        if (tiny_tiles) {
-            switch (h->radius) {
+        switch (h->radius) {
 #define X(R) case R: return launch_fast_rt<R, 8, true, 32>(h, p, want_tma, rows);
                 KDME_FAST_RADII(X)
 #undef X
