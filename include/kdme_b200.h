@@ -129,8 +129,7 @@ int jbf_upsample(jbf_handle *h, const float *depth_lo_dev, int wl, int hl, const
 
 /* Which kernel the handle selected: 0 = register-tiled fast path, 1 = generic path
  * (exotic sigmas / radius); bit 8 (0x100) set when the last launch staged tiles by TMA,
- * bit 9 (0x200) when it used 64x8 tiles (small launches) instead of 64x16, bit 10 (0x400) for the
- * packed fp32x2 math form. */
+ * bit 9 (0x200) when it used 64x8 tiles (small launches) instead of 64x16. */
 int jbf_kernel_variant(jbf_handle *h);
 
 /* "Next" row f1: MarkovRandomField::Process (MarkovRandomField.cu:4-49), raw guide. */

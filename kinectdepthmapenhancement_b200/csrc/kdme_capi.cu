@@ -322,9 +322,10 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
 }
 
 // One (radius, tile height) instantiation: encode the TMA maps for its box and launch.
-template <int R, int TH, bool PACKED, int TW = 64>
+template <int R, int TH, bool PACKED>
 static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
-    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : (TW == 64 ? 4 : 8);
+    constexpr int TW = 64;
+    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : 4;
     using T = JbfTile<R, TW, TH>;
     auto kern = jbf_fast_kernel<R, TW, TH, MINB, PACKED>;
     static bool attr_done[64] = {};
@@ -341,8 +342,7 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
                              (long long)p.guide_pitch * 4, (long long)p.guide_pitch * rows * 4, T::SP, T::SH);
         if (ok) p.mode = kStageTma;
     }
-    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (PACKED ? 0x400 : 0) |
-                      (TW == 32 ? 0x800 : 0);
+    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (PACKED ? 0x400 : 0);
     dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
     kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
     CK(cudaGetLastError());
@@ -387,12 +387,6 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
         // y_off/out_rows and always use 64x16.
         const long long ctas16 = (long long)((h->width + 63) / 64) * ((out_rows + 15) / 16) * n;
         const bool small_tiles = (ctas16 < 4LL * 148 * 3) && (rows == out_rows) && !h->force_big_tiles;
-        switch (h->radius) {
-#define X(R) case R: return launch_fast_rt<R, 8, true, 32>(h, p, want_tma, rows);
-                KDME_FAST_RADII(X)
-#undef X
-            }
-        }
         switch (h->radius) {
 #define X(R) case R: return h->scalar_math ? (small_tiles ? launch_fast_rt<R, 8, false>(h, p, want_tma, rows) : launch_fast_rt<R, 16, false>(h, p, want_tma, rows)) \
                                            : (small_tiles ? launch_fast_rt<R, 8, true>(h, p, want_tma, rows) : launch_fast_rt<R, 16, true>(h, p, want_tma, rows));
@@ -608,7 +602,7 @@ extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
     return h->smooth_bgr;
 }
 
-extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0xf00)) : -1; }
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x700)) : -1; }
 
 // ------------------------------------------------------------------ MRF (next row f1)
 extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,
