@@ -225,7 +225,8 @@ extern "C" int jbf_create(jbf_handle** out, int width, int height, float sigma_s
     if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "jbf_create: width/height must be positive");
     if (window_radius < 0 || window_radius > KDME_MAX_RADIUS)
         return fail(KDME_EINVAL, "jbf_create: window_radius must be in [0, 15]");
-    if (max_batch < 1) return fail(KDME_EINVAL, "jbf_create: max_batch must be >= 1");
+    if (max_batch < 1 || max_batch > 65535)
+        return fail(KDME_EINVAL, "jbf_create: max_batch must be in [1, 65535] (frames are grid.z of one launch)");
     if (!(sigma_spatial == sigma_spatial) || !(sigma_color == sigma_color) || !(sigma_depth == sigma_depth) ||
         sigma_spatial < 0 || sigma_color < 0 || sigma_depth < 0)
         return fail(KDME_EINVAL, "jbf_create: sigmas must be non-negative numbers");
