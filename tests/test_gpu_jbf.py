@@ -274,6 +274,8 @@ def test_argument_errors():
         JBF(64, 48, window_radius=16)
     with pytest.raises(KdmeError):
         JBF(64, 48, color_sigma=-1.0)
+    with pytest.raises(KdmeError):
+        JBF(64, 48, max_batch=70000)
     f = JBF(64, 48)
     with pytest.raises(TypeError):
         f.Process(torch.zeros(48, 64), torch.zeros(48, 64, 3, dtype=torch.uint8))   # CPU tensors
