@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config1", action="store_true",
+                    help="configs[0] instead of the headline line: the bundled 640x480 frame, reference defaults "
+                         "(window 5, 70/50/20), timed on the host cores and on the GPU, with parity figures")
     return ap.parse_args()
 
 
@@ -204,9 +207,64 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def run_config1(args):
+    """configs[0]: bundled input/color.jpg (+ surrogate depth: input/depth.xml is a stripped blob in the
+    reference checkout), JointBilateralFilter with the reference's defaults, on CPU host cores; the same
+    frame through the GPU path beside it, with the parity figures."""
+    import cv2
+    import numpy as np
+    import torch
+    import oracle
+    from kinectdepthmapenhancement_b200 import JointBilateralFilter, synth
+    oracle.build()
+    img = cv2.imread(os.path.join(ROOT, "tests", "golden", "guide_frame_640x480.png"), 1)
+    depth = synth.rgbd_frame(W, H, seed=2013, frame=0)[0].numpy()
+    kind = "reference" if oracle.ref_available() else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    cores = oracle.n_cores()
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < min(args.cpu_seconds, 10.0) or reps < 3:
+        guide = oracle.presmooth(img)
+        cpu_out = oracle.jbf(depth, guide, 5, 70.0, 50.0, 20.0, precision="f32", impl=impl, threads=cores)
+        reps += 1
+    cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    torch.cuda.set_device(0)
+    f = JointBilateralFilter(W, H)
+    d, c = torch.from_numpy(depth).cuda(), torch.from_numpy(img).cuda()
+    for _ in range(20):
+        f.Process(d, c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        f.Process(d, c)
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / 200
+    out = f.getFiltered_Device().cpu().numpy()
+    o64 = oracle.jbf(depth, guide, 5, 70.0, 50.0, 20.0, precision="f64")
+    err = np.abs(out.astype(np.float64) - o64)
+    e32 = np.abs(cpu_out.astype(np.float64) - o64)
+    print(json.dumps({
+        "workload": "configs[0]: bundled 640x480 colour frame + seeded surrogate depth (depth.xml unavailable: stripped "
+                    "blob), reference defaults window 5 / sigmas 70,50,20 / pre-smooth (5,30,30)",
+        "cpu": {"ms_per_frame": cpu_ms, "mpixel_s": W * H / cpu_ms / 1e3, "cores": cores, "kind": kind},
+        "gpu": {"us_per_frame_single_call": gpu_ms * 1e3, "mpixel_s": W * H / gpu_ms / 1e3},
+        "speedup_single_frame": cpu_ms / gpu_ms,
+        "parity": {"mask_bit_exact": bool(np.array_equal(out > 0, o64 > 0)),
+                   "presmooth_bit_exact": bool(np.array_equal(f.getSmoothImage_Device().cpu().numpy(), guide)),
+                   "gpu_vs_f64_max_abs_mm": float(err.max()), "gpu_within_1e-3mm": float((err <= 1e-3).mean()),
+                   "reference_fp32_vs_f64_max_abs_mm": float(e32.max()),
+                   "reference_fp32_within_1e-3mm": float((e32 <= 1e-3).mean())}}))
+
+
 # ------------------------------------------------------------------ this framework
 def main():
     args = parse()
+    if args.config1:
+        run_config1(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
