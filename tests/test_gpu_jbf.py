@@ -126,6 +126,17 @@ def test_tma_and_plain_staging_bit_identical():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_packed_and_scalar_math_bit_identical():
+    """FFMA2/FADD2 (packed fp32x2) compute the same bits per lane as the scalar FADD/FFMA form."""
+    depth, bgr = synth_np(320, 240, seed=8, frame=1)
+    guide = oracle.presmooth(bgr)
+    for r in (2, 7, 10):
+        a, va = gpu_filter(depth, guide, r)
+        b, vb = gpu_filter(depth, guide, r, env={"KDME_SCALAR_MATH": "1"})
+        assert (va & 0x400) and not (vb & 0x400)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 @pytest.mark.parametrize("ss,sc,sd,radius", [(70.0, 20.0, 20.0, 3),   # colour guard can fire (sigma_c < 30.6)
                                              (0.5, 50.0, 20.0, 3),    # spatial LUT underflows to 0 -> skipped
                                              (70.0, 0.0, 20.0, 2),    # sigma_c == 0: colour factor skipped
