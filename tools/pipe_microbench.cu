@@ -67,6 +67,14 @@ __global__ void __launch_bounds__(256) pipe_kernel(float* out, float a, float b,
                     asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(u[i]) : "r"(ua), "r"(0));
                     asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(a), "f"(b));
                 }
+                if (OP == 14) {  // FSETP (+ predicated FADD) interleaved with FFMA: does the compare share the FMA pipe?
+                    asm volatile("{ .reg .pred p; setp.gt.f32 p, %1, %2; @p fma.rn.f32 %0, %0, %3, %2; }"
+                                 : "+f"(x[i]) : "f"(x[(i + 1) % NCH]), "f"(b), "f"(a));
+                }
+                if (OP == 15) {  // plain FSETP chain only (predicate consumed by a select on the ALU pipe)
+                    asm volatile("{ .reg .pred p; setp.gt.f32 p, %1, %2; selp.u32 %0, %0, %3, p; }"
+                                 : "+r"(u[i]) : "f"(x[i]), "f"(b), "r"(ua));
+                }
                 if (OP == 8) {  // packed fp32x2 FMA (Blackwell FFMA2): counts as ONE instruction, two FMAs
                     unsigned long long v = pack2(x[i], x[(i + 4) % NCH]);
                     asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(pack2(a, a)), "l"(pack2(b, b)));
@@ -164,7 +172,8 @@ int main() {
     double ffma = run<0>(sms, 8, 1), fadd = run<1>(sms, 8, 1), mufu = run<2>(sms, 8, 1), vabs = run<3>(sms, 8, 1),
            idp = run<4>(sms, 8, 1), tap1 = run<5>(sms, 8, 1), tap2 = run<6>(sms, 8, 1), tap1lut = run<7>(sms, 8, 1),
            ffma2 = run<8>(sms, 8, 1), tap1x2 = run<9>(sms, 8, 1), i2fp = run<10>(sms, 8, 1), i2fp_ffma = run<11>(sms, 8, 1),
-           idp_ffma = run<12>(sms, 8, 1), vabs_ffma = run<13>(sms, 8, 1);
+           idp_ffma = run<12>(sms, 8, 1), vabs_ffma = run<13>(sms, 8, 1), fsetp_ffma = run<14>(sms, 8, 1),
+           fsetp_sel = run<15>(sms, 8, 1);
     // LDS.128
     float* d; cudaMalloc(&d, 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -179,11 +188,11 @@ int main() {
            "\"ffma_tflops\": %.2f, \"ffma_ginst_s\": %.1f, \"fadd_ginst_s\": %.1f, \"mufu_ex2_ginst_s\": %.1f, "
            "\"vabsdiff4_ginst_s\": %.1f, \"idp4a_ginst_s\": %.1f, \"tap_pass1_gtaps_s\": %.1f, \"tap_pass2_gtaps_s\": %.1f, "
            "\"tap_pass1_channel_lut_gtaps_s\": %.1f, \"ffma2_ginst_s\": %.1f, \"tap_pass1_f32x2_gtaps_s\": %.1f, \"lds128_tb_s\": %.2f, "
-           "\"i2fp_ginst_s\": %.1f, \"i2fp_plus_ffma_gpairs_s\": %.1f, \"idp4a_plus_ffma_gpairs_s\": %.1f, \"vabsdiff4_plus_ffma_gpairs_s\": %.1f, "
+           "\"i2fp_ginst_s\": %.1f, \"i2fp_plus_ffma_gpairs_s\": %.1f, \"idp4a_plus_ffma_gpairs_s\": %.1f, \"vabsdiff4_plus_ffma_gpairs_s\": %.1f, \"fsetp_plus_pred_ffma_gpairs_s\": %.1f, \"fsetp_plus_sel_gpairs_s\": %.1f, "
            "\"ffma_per_clk_per_sm\": %.1f, \"mufu_per_clk_per_sm\": %.1f, \"vabsdiff4_per_clk_per_sm\": %.1f, "
            "\"idp4a_per_clk_per_sm\": %.1f, \"how\": \"8 CTAs x 256 thr per SM, 8 independent chains, best of 5, per-clk at max clock\"}\n",
            p.name, sms, clk_khz / 1e3, 2 * ffma / 1e12, ffma / 1e9, fadd / 1e9, mufu / 1e9, vabs / 1e9, idp / 1e9,
-           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, ffma2 / 1e9, tap1x2 / 1e9, lds_bytes / 1e12, i2fp / 1e9, i2fp_ffma / 1e9, idp_ffma / 1e9, vabs_ffma / 1e9, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
+           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, ffma2 / 1e9, tap1x2 / 1e9, lds_bytes / 1e12, i2fp / 1e9, i2fp_ffma / 1e9, idp_ffma / 1e9, vabs_ffma / 1e9, fsetp_ffma / 1e9, fsetp_sel / 1e9, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
            vabs / (sms * clk_khz * 1e3), idp / (sms * clk_khz * 1e3));
     return 0;
 }
