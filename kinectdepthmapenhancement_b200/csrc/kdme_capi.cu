@@ -326,7 +326,7 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
 template <int R, int TH, bool PACKED>
 static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
     constexpr int TW = 64;
-    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : 4;
+    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : ((R <= 9) ? 6 : 4);  // 64x8: 600 CTAs of one Kinect frame must be co-resident (>= 5/SM)
     using T = JbfTile<R, TW, TH>;
     auto kern = jbf_fast_kernel<R, TW, TH, MINB, PACKED>;
     static bool attr_done[64] = {};
