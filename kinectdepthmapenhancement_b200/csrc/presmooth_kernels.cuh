@@ -92,17 +92,16 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
 }
 
 // ksize == 5 (the reference's call): 13 taps fully unrolled, 4 pixels per thread along x.  Each
-// staged pixel is converted ONCE to the pairs {float b, float g} and {float r, 1.0f} plus a packed
-// u8x4 word, kept as shared-memory planes so a thread fetches its 12-column row segment with
-// conflict-free 16-byte LDS; a tap is then VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL +
-// two FFMA2: {s_b, s_g} += w*{b, g} and {s_r, w_sum} += w*{r, 1} (w*1 is exact, so the weight sum is
-// the same sequence of rounded additions as a plain FADD chain).
+// staged pixel is converted ONCE to float b, g, r and a packed u8x4 word, kept as four shared-memory
+// planes so a thread fetches its 8-column row segment with conflict-free 16-byte LDS; a tap is then
+// VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
 template <int TW, int TH>
 __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const PresmoothParams p) {
     constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
     constexpr int XO = 4 - R;                                               // first used column of a staged row
-    __shared__ __align__(16) float2 sBG[SP * SH];
-    __shared__ __align__(16) float2 sR1[SP * SH];
+    __shared__ __align__(16) float sB[SP * SH];
+    __shared__ __align__(16) float sG[SP * SH];
+    __shared__ __align__(16) float sR[SP * SH];
     __shared__ __align__(16) uint32_t sP[SP * SH];
     __shared__ float sCol[768];
     __shared__ float sSp[25];
@@ -111,8 +110,6 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
     constexpr int SW = TW + 2 * R;   // staged (used) columns per row
     constexpr int NIT = (SW * SH + NT - 1) / NT;
-    // reflect-101 only matters for tiles that touch the image border (CTA-uniform)
-    const bool interior = (x0 >= R) && (y0 >= R) && (x0 + TW + R <= p.width) && (y0 + TH + R <= p.height);
     {   // all byte loads of the thread are issued before the first use (memory-level parallelism)
         uint32_t vb[NIT], vg[NIT], vr[NIT];
 #pragma unroll
@@ -121,8 +118,7 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
             vb[it] = vg[it] = vr[it] = 0u;
             if (idx < SW * SH) {
                 int sy = idx / SW, sx = idx - sy * SW;
-                int gx = x0 - R + sx, gy = y0 - R + sy;
-                if (!interior) { gx = reflect101(gx, p.width); gy = reflect101(gy, p.height); }
+                int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
                 const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
                 vb[it] = __ldg(q); vg[it] = __ldg(q + 1); vr[it] = __ldg(q + 2);
             }
@@ -133,8 +129,7 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
             if (idx < SW * SH) {
                 int sy = idx / SW, sx = idx - sy * SW;
                 const int o = sy * SP + XO + sx;
-                sBG[o] = make_float2((float)vb[it], (float)vg[it]);
-                sR1[o] = make_float2((float)vr[it], 1.0f);
+                sB[o] = (float)vb[it]; sG[o] = (float)vg[it]; sR[o] = (float)vr[it];
                 sP[o] = vb[it] | (vg[it] << 8) | (vr[it] << 16);
             }
         }
@@ -145,7 +140,8 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
 
     const int lx = tid % (TW / 4), ly = tid / (TW / 4);
     uint32_t c[4];
-    f32x2 sbg[4] = {0ull, 0ull, 0ull, 0ull}, srw[4] = {0ull, 0ull, 0ull, 0ull};
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f},
+          ws[4] = {0.f, 0.f, 0.f, 0.f};
     {
         const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (ly + R) * SP + 4 * lx + 4);
         c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
@@ -153,19 +149,18 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
 #pragma unroll
     for (int dy = 0; dy < 5; ++dy) {
         // columns [4*lx, 4*lx + 12) of the staged row: pixel k, tap dx sits at local column XO + k + dx
-        f32x2 rbg[12], rr1[12];
+        float rb[12], rg[12], rr[12];
         uint32_t rp[12];
         const int base = (ly + dy) * SP + 4 * lx;
 #pragma unroll
-        for (int v = 0; v < 6; ++v) {
-            const float4 a4 = *reinterpret_cast<const float4*>(sBG + base + 2 * v);
-            const float4 b4 = *reinterpret_cast<const float4*>(sR1 + base + 2 * v);
-            rbg[2 * v] = pack2(a4.x, a4.y); rbg[2 * v + 1] = pack2(a4.z, a4.w);
-            rr1[2 * v] = pack2(b4.x, b4.y); rr1[2 * v + 1] = pack2(b4.z, b4.w);
-        }
-#pragma unroll
         for (int v = 0; v < 3; ++v) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sB + base + 4 * v);
+            const float4 g4 = *reinterpret_cast<const float4*>(sG + base + 4 * v);
+            const float4 r4 = *reinterpret_cast<const float4*>(sR + base + 4 * v);
             const uint4 p4 = *reinterpret_cast<const uint4*>(sP + base + 4 * v);
+            rb[4 * v] = b4.x; rb[4 * v + 1] = b4.y; rb[4 * v + 2] = b4.z; rb[4 * v + 3] = b4.w;
+            rg[4 * v] = g4.x; rg[4 * v + 1] = g4.y; rg[4 * v + 2] = g4.z; rg[4 * v + 3] = g4.w;
+            rr[4 * v] = r4.x; rr[4 * v + 1] = r4.y; rr[4 * v + 2] = r4.z; rr[4 * v + 3] = r4.w;
             rp[4 * v] = p4.x; rp[4 * v + 1] = p4.y; rp[4 * v + 2] = p4.z; rp[4 * v + 3] = p4.w;
         }
 #pragma unroll
@@ -178,9 +173,10 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
                 const uint32_t ad = __vabsdiffu4(rp[col], c[k]);
                 const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
                 const float w = __fmul_rn(sw, sCol[l1]);
-                const f32x2 w2 = pack2(w, w);
-                sbg[k] = fma2(w2, rbg[col], sbg[k]);
-                srw[k] = fma2(w2, rr1[col], srw[k]);
+                s0[k] = __fmaf_rn(w, rb[col], s0[k]);
+                s1[k] = __fmaf_rn(w, rg[col], s1[k]);
+                s2[k] = __fmaf_rn(w, rr[col], s2[k]);
+                ws[k] = __fadd_rn(ws[k], w);
             }
         }
     }
@@ -189,12 +185,9 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float s0, s1, s2, ws;
-        unpack2(sbg[k], s0, s1);
-        unpack2(srw[k], s2, ws);
-        const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0, ws)), 0.f), 255.f);
-        const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1, ws)), 0.f), 255.f);
-        const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2, ws)), 0.f), 255.f);
+        const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0[k], ws[k])), 0.f), 255.f);
+        const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1[k], ws[k])), 0.f), 255.f);
+        const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2[k], ws[k])), 0.f), 255.f);
         o[k] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
     }
     uint32_t* dst = p.guide4 + (long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx;
