@@ -110,6 +110,8 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
     constexpr int SW = TW + 2 * R;   // staged (used) columns per row
     constexpr int NIT = (SW * SH + NT - 1) / NT;
+    // reflect-101 only matters for tiles that touch the image border (CTA-uniform)
+    const bool interior = (x0 >= R) && (y0 >= R) && (x0 + TW + R <= p.width) && (y0 + TH + R <= p.height);
     {   // all byte loads of the thread are issued before the first use (memory-level parallelism)
         uint32_t vb[NIT], vg[NIT], vr[NIT];
 #pragma unroll
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
             vb[it] = vg[it] = vr[it] = 0u;
             if (idx < SW * SH) {
                 int sy = idx / SW, sx = idx - sy * SW;
-                int gx = reflect101(x0 - R + sx, p.width), gy = reflect101(y0 - R + sy, p.height);
+                int gx = x0 - R + sx, gy = y0 - R + sy;
+                if (!interior) { gx = reflect101(gx, p.width); gy = reflect101(gy, p.height); }
                 const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
                 vb[it] = __ldg(q); vg[it] = __ldg(q + 1); vr[it] = __ldg(q + 2);
             }
