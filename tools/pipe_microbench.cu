@@ -141,18 +141,19 @@ __global__ void __launch_bounds__(256) lds_kernel(float* out, int iters) {
 }
 
 template <int OP>
-static double run(int sms, int ctas_per_sm, double ops_per_inner) {
+static double run(int sms, int ctas_per_sm, double ops_per_inner, int dyn_smem = 0) {
     float* d;
     cudaMalloc(&d, 16);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int grid = sms * ctas_per_sm;
-    pipe_kernel<OP><<<grid, 256>>>(d, 1.0001f, 0.5f, 0x01020304u, 64);
+    if (dyn_smem > 0) cudaFuncSetAttribute(pipe_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    pipe_kernel<OP><<<grid, 256, dyn_smem>>>(d, 1.0001f, 0.5f, 0x01020304u, 64);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < 5; r++) {
         cudaEventRecord(e0);
-        pipe_kernel<OP><<<grid, 256>>>(d, 1.0001f, 0.5f, 0x01020304u, ITERS);
+        pipe_kernel<OP><<<grid, 256, dyn_smem>>>(d, 1.0001f, 0.5f, 0x01020304u, ITERS);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -174,6 +175,10 @@ int main() {
            ffma2 = run<8>(sms, 8, 1), tap1x2 = run<9>(sms, 8, 1), i2fp = run<10>(sms, 8, 1), i2fp_ffma = run<11>(sms, 8, 1),
            idp_ffma = run<12>(sms, 8, 1), vabs_ffma = run<13>(sms, 8, 1), fsetp_ffma = run<14>(sms, 8, 1),
            fsetp_sel = run<15>(sms, 8, 1);
+    // occupancy sensitivity of the MUFU-heavy tap bodies: 3 resident CTAs (24 warps/SM, as the filter kernel
+    // runs) vs 8 (64 warps/SM); 72 KB of dynamic shared memory per CTA caps residency at 3
+    double tap1x2_24w = run<9>(sms, 24, 1, 72 * 1024), tap2_24w = run<6>(sms, 24, 1, 72 * 1024),
+           tap1x2_40w = run<9>(sms, 20, 1, 44 * 1024);
     // LDS.128
     float* d; cudaMalloc(&d, 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -188,11 +193,11 @@ int main() {
            "\"ffma_tflops\": %.2f, \"ffma_ginst_s\": %.1f, \"fadd_ginst_s\": %.1f, \"mufu_ex2_ginst_s\": %.1f, "
            "\"vabsdiff4_ginst_s\": %.1f, \"idp4a_ginst_s\": %.1f, \"tap_pass1_gtaps_s\": %.1f, \"tap_pass2_gtaps_s\": %.1f, "
            "\"tap_pass1_channel_lut_gtaps_s\": %.1f, \"ffma2_ginst_s\": %.1f, \"tap_pass1_f32x2_gtaps_s\": %.1f, \"lds128_tb_s\": %.2f, "
-           "\"i2fp_ginst_s\": %.1f, \"i2fp_plus_ffma_gpairs_s\": %.1f, \"idp4a_plus_ffma_gpairs_s\": %.1f, \"vabsdiff4_plus_ffma_gpairs_s\": %.1f, \"fsetp_plus_pred_ffma_gpairs_s\": %.1f, \"fsetp_plus_sel_gpairs_s\": %.1f, "
+           "\"i2fp_ginst_s\": %.1f, \"i2fp_plus_ffma_gpairs_s\": %.1f, \"idp4a_plus_ffma_gpairs_s\": %.1f, \"vabsdiff4_plus_ffma_gpairs_s\": %.1f, \"fsetp_plus_pred_ffma_gpairs_s\": %.1f, \"fsetp_plus_sel_gpairs_s\": %.1f, \"tap_pass1_f32x2_gtaps_s_24warps\": %.1f, \"tap_pass2_gtaps_s_24warps\": %.1f, \"tap_pass1_f32x2_gtaps_s_40warps\": %.1f, "
            "\"ffma_per_clk_per_sm\": %.1f, \"mufu_per_clk_per_sm\": %.1f, \"vabsdiff4_per_clk_per_sm\": %.1f, "
            "\"idp4a_per_clk_per_sm\": %.1f, \"how\": \"8 CTAs x 256 thr per SM, 8 independent chains, best of 5, per-clk at max clock\"}\n",
            p.name, sms, clk_khz / 1e3, 2 * ffma / 1e12, ffma / 1e9, fadd / 1e9, mufu / 1e9, vabs / 1e9, idp / 1e9,
-           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, ffma2 / 1e9, tap1x2 / 1e9, lds_bytes / 1e12, i2fp / 1e9, i2fp_ffma / 1e9, idp_ffma / 1e9, vabs_ffma / 1e9, fsetp_ffma / 1e9, fsetp_sel / 1e9, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
+           tap1 / 1e9, tap2 / 1e9, tap1lut / 1e9, ffma2 / 1e9, tap1x2 / 1e9, lds_bytes / 1e12, i2fp / 1e9, i2fp_ffma / 1e9, idp_ffma / 1e9, vabs_ffma / 1e9, fsetp_ffma / 1e9, fsetp_sel / 1e9, tap1x2_24w / 1e9, tap2_24w / 1e9, tap1x2_40w / 1e9, ffma / (sms * clk_khz * 1e3), mufu / (sms * clk_khz * 1e3),
            vabs / (sms * clk_khz * 1e3), idp / (sms * clk_khz * 1e3));
     return 0;
 }
