@@ -165,6 +165,15 @@ int kdme_guided_fill(const float *depth_dev, const int32_t *labels_dev, const ui
                      size_t bgr_step, float *out_dev, int width, int height, int window_radius,
                      float sigma_spatial, float sigma_color, float sigma_depth, void *stream);
 
+/* Label-guided upsampling ("a5 label-guided variant when labels are supplied"):
+ * the wl x hl low-res depth is scattered onto its high-res sites while tiles are staged (never
+ * materialised) and the depthmap_enhancement sweeps (EdgeRefinedSuperpixel.cu:104-205) run at the
+ * high-res size with the high-res label map (nullable) and RAW high-res guide. */
+int kdme_guided_upsample(const float *depth_lo_dev, int wl, int hl, const int32_t *labels_hi_dev,
+                         const uint8_t *bgr_hi_dev, size_t bgr_step, float *out_hi_dev, int width, int height,
+                         int window_radius, float sigma_spatial, float sigma_color, float sigma_depth,
+                         void *stream);
+
 /* ========================= ArrayBuffer / Buffer2D ========================= */
 typedef struct buf2d_handle buf2d_handle;
 

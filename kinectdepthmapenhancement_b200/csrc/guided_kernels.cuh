@@ -28,8 +28,20 @@ struct GuidedParams {
     long long bgr_step;
     float* out;
     float sigma_c, sigma_d;
+    // upsampling form (label-guided variant): when depth_lo != nullptr the depth
+    // plane is the sparse scatter of a wl x hl low-res map (see upsample_site) and `depth` is ignored
+    const float* depth_lo;
+    int wl, hl;
     float spatial[31 * 31];  // the reference's fp32 LUT (EdgeRefinedSuperpixel.cpp:46-55)
 };
+
+// low-res sample index landing on high-res coordinate x, or -1: x_hi(xl) = floor((2 xl + 1) * W / (2 wl))
+__device__ __forceinline__ int guided_upsample_site(int x, int W, int wl) {
+    long long num = 2LL * wl * x - W;
+    int xl = (num <= 0) ? 0 : (int)((num + 2LL * W - 1) / (2LL * W));
+    if (xl >= wl) return -1;
+    return ((int)(((2LL * xl + 1) * W) / (2LL * wl)) == x) ? xl : -1;
+}
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_constant__ GuidedParams p) {
@@ -51,7 +63,12 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_const
         int32_t l = 0;
         if (in) {
             const long long k = (long long)gy * p.width + gx;
-            d = __ldg(p.depth + k);
+            if (p.depth_lo) {
+                const int xl = guided_upsample_site(gx, p.width, p.wl), yl = guided_upsample_site(gy, p.height, p.hl);
+                if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
+            } else {
+                d = __ldg(p.depth + k);
+            }
             const uint8_t* q = p.bgr + (long long)gy * p.bgr_step + 3 * gx;
             g = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
             if (p.labels) l = __ldg(p.labels + k);

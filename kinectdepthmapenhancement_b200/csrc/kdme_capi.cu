@@ -688,6 +688,29 @@ extern "C" int kdme_mean_3d_error(const float* points_dev, const float* truth_de
 }
 
 // ------------------------------------------------------------------ guided fill
+static int guided_launch(const float* depth_dev, const float* depth_lo_dev, int wl, int hl, const int32_t* labels_dev,
+                         const uint8_t* bgr_dev, size_t bgr_step, float* out_dev, int width, int height,
+                         int window_radius, float sigma_spatial, float sigma_color, float sigma_depth, void* stream) {
+    if (bgr_step == 0) bgr_step = (size_t)3 * width;
+    if (bgr_step < (size_t)3 * width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
+    const int ws = 2 * window_radius + 1;
+    std::vector<float> lut;
+    host_spatial_lut(lut, ws, sigma_spatial);
+    GuidedParams p;
+    if (ws * ws > (int)(sizeof(p.spatial) / sizeof(float))) return fail(KDME_ENOTSUP, "guided fill: window too large");
+    for (int i = 0; i < ws * ws; i++) p.spatial[i] = lut[i];
+    p.width = width; p.height = height; p.radius = window_radius;
+    p.depth = depth_dev; p.labels = labels_dev; p.bgr = bgr_dev; p.bgr_step = (long long)bgr_step; p.out = out_dev;
+    p.sigma_c = sigma_color; p.sigma_d = sigma_depth;
+    p.depth_lo = depth_lo_dev; p.wl = wl; p.hl = hl;
+    constexpr int TW = 32, TH = 8;
+    const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
+    dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
+    guided_fill_kernel<TW, TH><<<grd, TW * TH, (size_t)SP * SH * 12, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
 extern "C" int kdme_guided_fill(const float* depth_dev, const int32_t* labels_dev, const uint8_t* bgr_dev,
                                 size_t bgr_step, float* out_dev, int width, int height, int window_radius,
                                 float sigma_spatial, float sigma_color, float sigma_depth, void* stream) {
@@ -695,22 +718,20 @@ extern "C" int kdme_guided_fill(const float* depth_dev, const int32_t* labels_de
     if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "kdme_guided_fill: bad size");
     if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "kdme_guided_fill: bad radius");
     if (depth_dev == out_dev) return fail(KDME_EINVAL, "kdme_guided_fill: in-place operation is not supported");
-    if (bgr_step == 0) bgr_step = (size_t)3 * width;
-    const int ws = 2 * window_radius + 1;
-    std::vector<float> lut;
-    host_spatial_lut(lut, ws, sigma_spatial);
-    GuidedParams p;
-    if (ws * ws > (int)(sizeof(p.spatial) / sizeof(float))) return fail(KDME_ENOTSUP, "kdme_guided_fill: window too large");
-    for (int i = 0; i < ws * ws; i++) p.spatial[i] = lut[i];
-    p.width = width; p.height = height; p.radius = window_radius;
-    p.depth = depth_dev; p.labels = labels_dev; p.bgr = bgr_dev; p.bgr_step = (long long)bgr_step; p.out = out_dev;
-    p.sigma_c = sigma_color; p.sigma_d = sigma_depth;
-    constexpr int TW = 32, TH = 8;
-    const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
-    dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
-    guided_fill_kernel<TW, TH><<<grd, TW * TH, (size_t)SP * SH * 12, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
-    return KDME_OK;
+    return guided_launch(depth_dev, nullptr, 0, 0, labels_dev, bgr_dev, bgr_step, out_dev, width, height, window_radius,
+                         sigma_spatial, sigma_color, sigma_depth, stream);
+}
+
+extern "C" int kdme_guided_upsample(const float* depth_lo_dev, int wl, int hl, const int32_t* labels_hi_dev,
+                                    const uint8_t* bgr_hi_dev, size_t bgr_step, float* out_hi_dev, int width,
+                                    int height, int window_radius, float sigma_spatial, float sigma_color,
+                                    float sigma_depth, void* stream) {
+    if (!depth_lo_dev || !bgr_hi_dev || !out_hi_dev) return fail(KDME_EINVAL, "kdme_guided_upsample: NULL argument");
+    if (width <= 0 || height <= 0 || wl <= 0 || hl <= 0 || wl > width || hl > height)
+        return fail(KDME_EINVAL, "kdme_guided_upsample: low-res size must be positive and <= the high-res size");
+    if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "kdme_guided_upsample: bad radius");
+    return guided_launch(nullptr, depth_lo_dev, wl, hl, labels_hi_dev, bgr_hi_dev, bgr_step, out_hi_dev, width, height,
+                         window_radius, sigma_spatial, sigma_color, sigma_depth, stream);
 }
 
 // ------------------------------------------------------------------ Buffer2D

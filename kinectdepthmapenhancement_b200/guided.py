@@ -32,3 +32,28 @@ def guided_fill(depth: torch.Tensor, color: torch.Tensor, labels: torch.Tensor |
                                                _ptr(color), 3 * w, _ptr(out), w, h, window_radius, spatial_sigma,
                                                color_sigma, depth_sigma, torch.cuda.current_stream().cuda_stream))
     return out
+
+
+def guided_upsample(depth_lo: torch.Tensor, color_hi: torch.Tensor, labels_hi: torch.Tensor | None = None,
+                    window_radius: int = 7, spatial_sigma: float = SpatialSigma, color_sigma: float = ColorSigma,
+                    depth_sigma: float = DepthSigma, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Label-guided upsampling: low-res depth [hl,wl] -> high-res [H,W] using the
+    depthmap_enhancement sweeps with the high-res label map (or None) and RAW high-res guide."""
+    dev = depth_lo.device
+    _check_cuda(depth_lo, torch.float32, "depth_lo", dev)
+    _check_cuda(color_hi, torch.uint8, "color_hi", dev)
+    hl, wl = depth_lo.shape
+    h, w, _ = color_hi.shape
+    if labels_hi is not None:
+        _check_cuda(labels_hi, torch.int32, "labels_hi", dev)
+        if tuple(labels_hi.shape) != (h, w):
+            raise ValueError("labels must be [H,W] at the high-res size")
+    if out is None:
+        out = torch.empty((h, w), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().kdme_guided_upsample(_ptr(depth_lo), wl, hl,
+                                                   _ptr(labels_hi) if labels_hi is not None else None,
+                                                   _ptr(color_hi), 3 * w, _ptr(out), w, h, window_radius,
+                                                   spatial_sigma, color_sigma, depth_sigma,
+                                                   torch.cuda.current_stream().cuda_stream))
+    return out

@@ -129,3 +129,26 @@ def test_guided_fill_full_size_properties():
     const = torch.where(d > 50, torch.full_like(d, 1500.25), torch.zeros_like(d))
     oc = guided_fill(const, c, None, r)
     assert torch.all((oc[oc > 0] - 1500.25).abs() <= 2.5e-4)
+
+
+def test_guided_upsample_matches_oracle():
+    """Config 3, label-guided variant: scatter fused into staging == oracle fill of the materialised sparse image."""
+    from kinectdepthmapenhancement_b200.guided import guided_upsample
+    from kinectdepthmapenhancement_b200 import guided_fill, synth
+    wl, hl, wh, hh, r = 96, 80, 360, 204, 5
+    lo, _ = synth.rgbd_frame(wl, hl, seed=6, frame=2, noise_rel=0.01)
+    _, hi = synth.rgbd_frame(wh, hh, seed=6, frame=2)
+    labels = ((np.arange(hh)[:, None] // 24) * 64 + (np.arange(wh)[None, :] // 30)).astype(np.int32)
+    got = guided_upsample(lo.cuda(), hi.cuda(), torch.from_numpy(labels).cuda(), r).cpu().numpy()
+    sparse = oracle.scatter_lowres(lo.numpy(), wh, hh)
+    o64 = oracle.guided_fill(sparse, hi.numpy(), labels, 2 * r + 1, precision="f64")
+    o32 = oracle.guided_fill(sparse, hi.numpy(), labels, 2 * r + 1)
+    assert np.array_equal(np.isnan(got), np.isnan(o64))
+    ok = ~np.isnan(o64)
+    assert np.array_equal(got[ok] > 0, o64[ok] > 0)
+    err = np.abs(got[ok].astype(np.float64) - o64[ok])
+    e32 = np.abs(o32[ok].astype(np.float64) - o64[ok])
+    assert np.median(err) <= 2.5e-4 and np.quantile(err, 0.99) <= max(1e-3, np.quantile(e32, 0.99))
+    # identical to the same-resolution fill of the materialised sparse image
+    dense = guided_fill(torch.from_numpy(sparse).cuda(), hi.cuda(), torch.from_numpy(labels).cuda(), r).cpu().numpy()
+    assert np.array_equal(np.nan_to_num(dense, nan=-1).view(np.uint32), np.nan_to_num(got, nan=-1).view(np.uint32))
