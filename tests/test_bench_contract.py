@@ -1,0 +1,54 @@
+"""bench.py contract: the reference arm runs on host cores only and prints the required JSON line;
+the GPU arm's line is checked on the GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"]
+
+
+def _run(args, timeout=600):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, "bench.py must print exactly one JSON line"
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    line = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    for k in REQUIRED + ["impl", "cpu_baseline"]:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "Mpixel/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_reference_arm_non_zero_rank_is_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line():
+    line = _run(["--frames", "256", "--steps", "2", "--warmup", "3", "--e2e-frames", "128", "--cpu-seconds", "3"])
+    for k in REQUIRED + ["roofline", "cpu_baseline", "clocks"]:
+        assert k in line, k
+    rf = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in rf, k
+    assert 0.3 < rf["frac"] < 1.2 and rf["hbm"]["frac"] < 0.1      # compute-bound stencil
+    assert line["gpu_launches"] == 2 * 2 * 4                        # 2 steps x (256/64 chunks) x 2 kernels
+    assert line["e2e"]["h2d_bytes_per_step"] == 128 * 640 * 480 * 7 and line["e2e"]["d2h_bytes_per_step"] == 128 * 640 * 480 * 4
+    assert line["scaling"] == "weak" and line["vs_baseline"] is None and line["dtype"] == "f32"
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
