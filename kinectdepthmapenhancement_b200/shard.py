@@ -141,6 +141,7 @@ class RowBandJBF:
         self.pitch = (width + 3) & ~3
         self.guide4 = torch.empty((p.ext_rows, self.pitch), dtype=torch.int32, device=self.device)
         self.out = torch.empty((p.band_rows, width), dtype=torch.float32, device=self.device)
+        self._strip = None
 
     @property
     def depth_band(self):
@@ -150,15 +151,60 @@ class RowBandJBF:
     def bgr_band(self):
         return self.halo.bgr_band
 
-    def process(self, exchange: bool = True) -> torch.Tensor:
+    def _presmooth(self, row0: int, rows: int, keep0: int | None = None, keep1: int | None = None) -> None:
+        """Pre-smooth ext rows [row0, row0 + rows) (reflect-101 at the slice ends).  Without keep0/keep1 all of
+        them are written into guide4; with them the slice is smoothed into a scratch strip and only rows
+        [keep0, keep1) are copied over (the slice's own two end rows are reflect-contaminated)."""
         from . import _lib
         p = self.plan
-        if exchange:
-            self.halo.exchange()
-        L = _lib.lib()
-        h = self.jbf._h
-        _lib.check(L.jbf_presmooth_rows(h, self.halo.bgr_ext.data_ptr(), 3 * p.width, self.guide4.data_ptr(),
-                                        self.pitch * 4, p.ext_rows))
-        _lib.check(L.jbf_filter_rows(h, self.halo.depth_ext.data_ptr(), self.guide4.data_ptr(), self.pitch * 4,
-                                     self.out.data_ptr(), p.ext_rows, p.up, p.band_rows))
+        if keep0 is None:
+            dst = self.guide4[row0:]
+        else:
+            if self._strip is None or self._strip.shape[0] < rows:
+                self._strip = torch.empty((rows, self.pitch), dtype=torch.int32, device=self.device)
+            dst = self._strip
+        _lib.check(_lib.lib().jbf_presmooth_rows(self.jbf._h, self.halo.bgr_ext[row0:].data_ptr(), 3 * p.width,
+                                                 dst.data_ptr(), self.pitch * 4, rows))
+        if keep0 is not None:
+            self.guide4[keep0:keep1].copy_(dst[keep0 - row0:keep1 - row0])
+
+    def _filter(self, y_off: int, out_rows: int) -> None:
+        from . import _lib
+        p = self.plan
+        _lib.check(_lib.lib().jbf_filter_rows(self.jbf._h, self.halo.depth_ext.data_ptr(), self.guide4.data_ptr(),
+                                              self.pitch * 4, self.out[y_off - p.up:].data_ptr(), p.ext_rows, y_off,
+                                              out_rows))
+
+    def process(self, exchange: bool = True, overlap: bool = True) -> torch.Tensor:
+        """Filter this rank's band.  With overlap=True the neighbour exchange runs while the band's interior
+        rows (those whose window and pre-smooth footprint stay inside the band) are filtered; the two seam
+        strips follow once the halos have landed.  Strips start on tile rows, so the result is bit-identical
+        to the unsplit launch and to the single-GPU frame."""
+        p = self.plan
+        edge = TILE_H * ((p.halo + TILE_H - 1) // TILE_H)          # seam strip height (tile multiple >= r + 2)
+        top = edge if p.up else 0
+        bot = edge if p.down else 0
+        if not (overlap and p.world > 1) or p.band_rows < top + bot + TILE_H:
+            if exchange:
+                self.halo.exchange()
+            self._presmooth(0, p.ext_rows)
+            self._filter(p.up, p.band_rows)
+            return self.out
+        works = self.halo.start() if exchange else []
+        # interior: pre-smooth the band alone (its two outermost rows are reflect-contaminated and are redone
+        # below); rows [up + top, up + band - bot_rows) only look at rows >= 2 inside the band
+        self._presmooth(p.up, p.band_rows)
+        bot_rows = bot + ((p.band_rows - top - bot) % TILE_H if bot else 0)   # keep the interior a tile multiple
+        interior = p.band_rows - top - bot_rows
+        self._filter(p.up + top, interior)
+        for w in works:
+            w.wait()
+        R2 = PRESMOOTH_RADIUS
+        if top:      # guide rows [0, up + 2) need the upper halo; rows from up + 2 on are already right
+            self._presmooth(0, p.up + 2 * R2, keep0=0, keep1=p.up + R2)
+            self._filter(p.up, top)
+        if bot:
+            r0 = p.up + p.band_rows - 2 * R2
+            self._presmooth(r0, p.ext_rows - r0, keep0=r0 + R2, keep1=p.ext_rows)
+            self._filter(p.up + p.band_rows - bot_rows, bot_rows)
         return self.out

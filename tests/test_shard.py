@@ -96,8 +96,9 @@ def test_halo_exchange_gloo(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,radius,world", [(256, 192, 9, 2), (320, 256, 7, 4), (128, 160, 3, 3)])
-def test_row_bands_equal_whole_frame_bit_for_bit(w, h, radius, world):
+@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("w,h,radius,world", [(256, 192, 9, 2), (320, 256, 7, 4), (128, 160, 3, 3), (192, 400, 15, 2)])
+def test_row_bands_equal_whole_frame_bit_for_bit(w, h, radius, world, overlap):
     """N ranks emulated one after another on one GPU (no waiting kernels): every rank's extended arrays
     are filled as the halo exchange would fill them, the band results are concatenated and must equal
     the single-GPU whole-frame result bit for bit."""
@@ -118,5 +119,5 @@ def test_row_bands_equal_whole_frame_bit_for_bit(w, h, radius, world):
         p = rb.plan
         rb.halo.depth_ext.copy_(d[p.y0 - p.up:p.y1 + p.down])
         rb.halo.bgr_ext.copy_(c[p.y0 - p.up:p.y1 + p.down])
-        got[p.y0:p.y1] = rb.process(exchange=False).cpu()
+        got[p.y0:p.y1] = rb.process(exchange=False, overlap=overlap).cpu()   # overlap: interior first, seam strips after
     assert torch.equal(got.view(torch.int32), want.view(torch.int32))
