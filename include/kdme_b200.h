@@ -93,6 +93,19 @@ int jbf_presmooth_rows(jbf_handle *h, const uint8_t *bgr_dev, size_t bgr_step, u
 int jbf_filter_rows(jbf_handle *h, const float *depth_dev, const uint8_t *guide4_dev, size_t guide_step,
                     float *out_dev, int rows, int y_off, int out_rows);
 
+/* Row bands with the halo rows read from the neighbour GPUs' memory INSIDE the kernels (NVLink peer
+ * loads on peer-mapped pointers, e.g. torch symmetric memory / CUDA IPC) -- no exchange step.  The arrays
+ * hold `rows` rows of which [band0, band1) are this rank's own; a row r < band0 is read from
+ * *_up + r * pitch and a row r >= band1 from *_dn + (r - band1) * pitch (either may be NULL at an image
+ * border).  Interior tiles keep TMA staging; the two seam tile-rows stage with plain loads.  Results are
+ * bit-identical to jbf_presmooth_rows / jbf_filter_rows on arrays whose halo rows were copied in. */
+int jbf_presmooth_rows_p2p(jbf_handle *h, const uint8_t *bgr_dev, size_t bgr_step, uint8_t *guide4_dev,
+                           size_t guide_step, int rows, int band0, int band1, const uint8_t *bgr_up,
+                           const uint8_t *bgr_dn);
+int jbf_filter_rows_p2p(jbf_handle *h, const float *depth_dev, const uint8_t *guide4_dev, size_t guide_step,
+                        float *out_dev, int rows, int y_off, int out_rows, int band0, int band1,
+                        const float *depth_up, const float *depth_dn);
+
 /* Host-buffer convenience used for end-to-end timing: pinned or pageable HOST
  * depth/bgr in, HOST filtered depth out; H2D, Process, D2H are pipelined in
  * chunks of at most max_batch frames.  Synchronous (returns when out_host is

@@ -51,6 +51,8 @@ SIGNATURES = {
     "jbf_process_host": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "jbf_presmooth_rows": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
     "jbf_filter_rows": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _i]),
+    "jbf_presmooth_rows_p2p": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _i, _vp, _vp]),
+    "jbf_filter_rows_p2p": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "jbf_filtered_device": (_vp, [_vp]),
     "jbf_filtered_host": (_vp, [_vp]),
     "jbf_smooth_device": (_vp, [_vp, C.POINTER(_sz)]),

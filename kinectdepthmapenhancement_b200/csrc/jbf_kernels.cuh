@@ -57,6 +57,13 @@ struct JbfParams {
     // band whose first image row is a multiple of the tile height is tiled exactly like the
     // whole image and the result is bit-identical.  Whole-image mode: y_off = 0, out_rows = height.
     int y_off, out_rows;
+    // peer-memory halos (row bands over NVLink): rows [band0, band1) of the arrays are this rank's own;
+    // when depth_up / depth_dn are non-null, rows above / below are read straight from the neighbour
+    // GPU's band through these peer-mapped pointers (depth_up + row*W for row < band0,
+    // depth_dn + (row - band1)*W for row >= band1) instead of from local halo copies.
+    const float* depth_up;
+    const float* depth_dn;
+    int band0, band1;
 };
 
 template <int R, int TW, int TH>
@@ -103,9 +110,13 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = p.y_off + blockIdx.y * TH, frame = blockIdx.z;
     const int sx0 = x0 - RP, sy0 = y0 - R;  // image coords of staged (0,0)
+    // a tile whose halo crosses into a neighbour GPU's rows stages with plain loads (peer pointers);
+    // every other tile keeps the launch's staging mode (CTA-uniform)
+    const bool seam = (p.depth_up != nullptr && sy0 < p.band0) || (p.depth_dn != nullptr && sy0 + SH > p.band1);
+    const int mode = seam ? (int)kStagePlain : p.mode;
 
     // ---------------- stage A: raw depth + guide tile with halo -> shared memory
-    if (p.mode == kStageTma) {
+    if (mode == kStageTma) {
         if (tid == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
@@ -123,7 +134,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         // (sM is free until stage B: its first SP + SH words hold the two maps)
         int* colmap = reinterpret_cast<int*>(sM);
         int* rowmap = colmap + SP;
-        if (p.mode == kStageUpsample) {
+        if (mode == kStageUpsample) {
             for (int t = tid; t < SP + SH; t += NT) {
                 if (t < SP) {
                     const int gx = sx0 + t;
@@ -143,8 +154,11 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             uint32_t g = 0u;
             if (in) {
                 g = __ldg(gsrc + (long long)gy * p.guide_pitch + gx);
-                if (p.mode == kStagePlain) {
-                    d = __ldg(dsrc + (long long)gy * p.width + gx);
+                if (mode == kStagePlain) {
+                    const float* row = dsrc + (long long)gy * p.width;
+                    if (p.depth_up != nullptr && gy < p.band0) row = p.depth_up + (long long)gy * p.width;
+                    else if (p.depth_dn != nullptr && gy >= p.band1) row = p.depth_dn + (long long)(gy - p.band1) * p.width;
+                    d = __ldg(row + gx);
                 } else {  // scatter the low-res sample onto its high-res site
                     const int xl = colmap[sx], yl = rowmap[sy];
                     if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
@@ -160,7 +174,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     } else {
         for (int idx = tid; idx < WS * LP; idx += NT) sL[idx] = __ldg(p.ltab + idx);
     }
-    if (p.mode == kStageTma) mbar_wait(bar, 0);
+    if (mode == kStageTma) mbar_wait(bar, 0);
     __syncthreads();
 
     // ---------------- stage B: validity, tile origin d_ref, scaled/shifted depth

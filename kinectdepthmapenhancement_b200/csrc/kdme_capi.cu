@@ -293,11 +293,13 @@ extern "C" int jbf_set_presmooth(jbf_handle* h, int ksize, float sigma_color, fl
 
 // ------------------------------------------------------------------ launches
 static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, uint32_t* guide4, int guide_pitch,
-                            int n, int rows = -1) {
+                            int n, int rows = -1, const uint8_t* bgr_up = nullptr, const uint8_t* bgr_dn = nullptr,
+                            int band0 = 0, int band1 = 0) {
     if (rows < 0) rows = h->height;
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
     if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
     if (h->ps_ksize == 0) {
+        if (bgr_up || bgr_dn) return fail(KDME_ENOTSUP, "peer-memory halos need the guide pre-smooth enabled");
         dim3 blk(128), grd((h->width + 127) / 128, rows, n);
         bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr, (long long)bgr_step, (long long)bgr_step * rows,
                                                          guide4, guide_pitch, (long long)guide_pitch * rows,
@@ -308,6 +310,7 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
         p.bgr = bgr; p.bgr_step = (long long)bgr_step; p.bgr_frame_stride = (long long)bgr_step * rows;
         p.guide4 = guide4; p.guide_pitch = guide_pitch; p.guide_frame_stride = (long long)guide_pitch * rows;
         p.ksize = h->ps_ksize; p.space_lut = h->ps_space_dev; p.color_lut = h->ps_color_dev;
+        p.bgr_up = bgr_up; p.bgr_dn = bgr_dn; p.band0 = band0; p.band1 = band1;
         if (h->ps_ksize == 5) {
             constexpr int TW = 64, TH = 8;
             dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
@@ -364,12 +367,16 @@ static bool fast_radius_available(int r) {
 
 static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guide4, int guide_pitch, float* out,
                          int n, int mode, const float* depth_lo, int wl, int hl, int rows = -1, int y_off = 0,
-                         int out_rows = -1) {
+                         int out_rows = -1, const float* depth_up = nullptr, const float* depth_dn = nullptr,
+                         int band0 = 0, int band1 = 0) {
     JbfParams p;
     if (rows < 0) rows = h->height;
     if (out_rows < 0) out_rows = rows;
     p.width = h->width; p.height = rows; p.n_frames = n;
     p.y_off = y_off; p.out_rows = out_rows;
+    p.depth_up = depth_up; p.depth_dn = depth_dn; p.band0 = band0; p.band1 = band1;
+    if ((depth_up || depth_dn) && !h->fast)
+        return fail(KDME_ENOTSUP, "peer-memory halos are implemented for the fast kernel (default sigmas, r = 1..15)");
     p.depth = depth; p.guide4 = guide4; p.out = out;
     p.depth_frame_stride = (long long)h->width * rows;
     p.guide_frame_stride = (long long)guide_pitch * rows;
@@ -463,6 +470,37 @@ extern "C" int jbf_filter_rows(jbf_handle* h, const float* depth_dev, const uint
     DeviceGuard g(h->device);
     return launch_filter(h, depth_dev, reinterpret_cast<const uint32_t*>(guide4_dev), (int)(guide_step / 4), out_dev, 1,
                          kStagePlain, nullptr, 0, 0, rows, y_off, out_rows);
+}
+
+// Row bands with the halos read from the neighbour GPUs' memory inside the kernels (NVLink peer loads):
+// the arrays hold `rows` rows of which [band0, band1) are this rank's own; *_up / *_dn are peer-mapped
+// pointers positioned so that row r < band0 is  up + r * pitch  and row r >= band1 is  dn + (r - band1) * pitch.
+extern "C" int jbf_presmooth_rows_p2p(jbf_handle* h, const uint8_t* bgr_dev, size_t bgr_step, uint8_t* guide4_dev,
+                                      size_t guide_step, int rows, int band0, int band1, const uint8_t* bgr_up,
+                                      const uint8_t* bgr_dn) {
+    if (!h || !bgr_dev || !guide4_dev) return fail(KDME_EINVAL, "jbf_presmooth_rows_p2p: NULL argument");
+    if (rows < 1 || band0 < 0 || band1 > rows || band0 >= band1)
+        return fail(KDME_EINVAL, "jbf_presmooth_rows_p2p: need 0 <= band0 < band1 <= rows");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_presmooth_rows_p2p: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_presmooth(h, bgr_dev, bgr_step, reinterpret_cast<uint32_t*>(guide4_dev), (int)(guide_step / 4), 1, rows,
+                            bgr_up, bgr_dn, band0, band1);
+}
+
+extern "C" int jbf_filter_rows_p2p(jbf_handle* h, const float* depth_dev, const uint8_t* guide4_dev, size_t guide_step,
+                                   float* out_dev, int rows, int y_off, int out_rows, int band0, int band1,
+                                   const float* depth_up, const float* depth_dn) {
+    if (!h || !depth_dev || !guide4_dev || !out_dev) return fail(KDME_EINVAL, "jbf_filter_rows_p2p: NULL argument");
+    if (rows < 1 || y_off < 0 || out_rows < 1 || y_off + out_rows > rows || band0 < 0 || band1 > rows || band0 >= band1)
+        return fail(KDME_EINVAL, "jbf_filter_rows_p2p: bad row ranges");
+    if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
+    if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
+        return fail(KDME_EINVAL, "jbf_filter_rows_p2p: guide_step must be a multiple of 4 and >= 4*width");
+    DeviceGuard g(h->device);
+    return launch_filter(h, depth_dev, reinterpret_cast<const uint32_t*>(guide4_dev), (int)(guide_step / 4), out_dev, 1,
+                         kStagePlain, nullptr, 0, 0, rows, y_off, out_rows, depth_up, depth_dn, band0, band1);
 }
 
 extern "C" int jbf_process_batch(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step,

@@ -33,7 +33,17 @@ struct PresmoothParams {
     int ksize;
     const float* space_lut;  // [ksize*ksize], < 0 outside the circle
     const float* color_lut;  // [766]
+    // peer-memory halos (see JbfParams): rows outside [band0, band1) come from the neighbour GPU's band
+    const uint8_t* bgr_up;   // row r < band0  -> bgr_up + r * bgr_step
+    const uint8_t* bgr_dn;   // row r >= band1 -> bgr_dn + (r - band1) * bgr_step
+    int band0, band1;
 };
+
+__device__ __forceinline__ const uint8_t* presmooth_row(const PresmoothParams& p, const uint8_t* src, int gy) {
+    if (p.bgr_up != nullptr && gy < p.band0) return p.bgr_up + (long long)gy * p.bgr_step;
+    if (p.bgr_dn != nullptr && gy >= p.band1) return p.bgr_dn + (long long)(gy - p.band1) * p.bgr_step;
+    return src + (long long)gy * p.bgr_step;
+}
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
@@ -58,7 +68,7 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
     for (int idx = tid; idx < SP * SH; idx += NT) {
         int sy = idx / SP, sx = idx - sy * SP;
         int gx = reflect101(x0 - r + sx, p.width), gy = reflect101(y0 - r + sy, p.height);
-        const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
+        const uint8_t* q = presmooth_row(p, src, gy) + 3 * gx;
         sPix[idx] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
     }
     for (int idx = tid; idx < 766; idx += NT) sCol[idx] = __ldg(p.color_lut + idx);
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
                 int sy = idx / SW, sx = idx - sy * SW;
                 int gx = x0 - R + sx, gy = y0 - R + sy;
                 if (!interior) { gx = reflect101(gx, p.width); gy = reflect101(gy, p.height); }
-                const uint8_t* q = src + (long long)gy * p.bgr_step + 3 * gx;
+                const uint8_t* q = presmooth_row(p, src, gy) + 3 * gx;
                 vb[it] = __ldg(q); vg[it] = __ldg(q + 1); vr[it] = __ldg(q + 2);
             }
         }

@@ -124,17 +124,65 @@ class HaloExchanger:
             w.wait()
 
 
+class PeerHalo:
+    """Band arrays in NVLink-mapped symmetric memory: no exchange step at all.  Every rank allocates its
+    extended arrays with torch symmetric memory, the ranks rendezvous once, and the kernels read the halo
+    rows directly from the neighbours' bands (peer loads in the staging code of the seam tiles).  The local
+    halo rows of the arrays are never written or read."""
+
+    def __init__(self, plan: BandPlan, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.plan = p = plan
+        group = group if group is not None else dist.group.WORLD
+        plans = [make_plan(p.width, p.height, p.radius, r, p.world) for r in range(p.world)]
+        max_rows = max(q.ext_rows for q in plans)
+        self._depth_flat = symm_mem.empty(max_rows * p.width, dtype=torch.float32, device=device)
+        self._bgr_flat = symm_mem.empty(max_rows * p.width * 3, dtype=torch.uint8, device=device)
+        self._hd = symm_mem.rendezvous(self._depth_flat, group=group)
+        self._hb = symm_mem.rendezvous(self._bgr_flat, group=group)
+        self.depth_ext = self._depth_flat[:p.ext_rows * p.width].view(p.ext_rows, p.width)
+        self.bgr_ext = self._bgr_flat[:p.ext_rows * p.width * 3].view(p.ext_rows, p.width, 3)
+        self.depth_band = self.depth_ext[p.up:p.up + p.band_rows]
+        self.bgr_band = self.bgr_ext[p.up:p.up + p.band_rows]
+        # peer-mapped views of the neighbours' whole symmetric buffers (kept alive here)
+        self._peers = {}
+        self.depth_up = self.depth_dn = self.bgr_up = self.bgr_dn = 0
+        if p.rank > 0:
+            q = plans[p.rank - 1]
+            d = self._hd.get_buffer(p.rank - 1, (max_rows * p.width,), torch.float32)
+            b = self._hb.get_buffer(p.rank - 1, (max_rows * p.width * 3,), torch.uint8)
+            self._peers["up"] = (d, b)
+            first = q.up + q.band_rows - p.up          # neighbour row that is my ext row 0
+            self.depth_up = d.data_ptr() + first * p.width * 4
+            self.bgr_up = b.data_ptr() + first * p.width * 3
+        if p.rank < p.world - 1:
+            q = plans[p.rank + 1]
+            d = self._hd.get_buffer(p.rank + 1, (max_rows * p.width,), torch.float32)
+            b = self._hb.get_buffer(p.rank + 1, (max_rows * p.width * 3,), torch.uint8)
+            self._peers["dn"] = (d, b)
+            self.depth_dn = d.data_ptr() + q.up * p.width * 4   # neighbour's first band row = my ext row band1
+            self.bgr_dn = b.data_ptr() + q.up * p.width * 3
+
+    def barrier(self):
+        """Device-side barrier across the ranks on the current stream: bands written / halo reads finished."""
+        self._hd.barrier()
+
+
 class RowBandJBF:
     """One rank's share of JointBilateralFilter::Process on a frame split into row bands."""
 
     def __init__(self, width, height, radius, rank, world, spatial_sigma=70.0, color_sigma=50.0, depth_sigma=20.0,
-                 device=None, group=None):
+                 device=None, group=None, peer_memory: bool = False):
+        """peer_memory=False: halos filled by one batched NCCL isend/irecv per frame (HaloExchanger).
+        peer_memory=True: bands live in NVLink-mapped symmetric memory and the kernels read the halo rows from
+        the neighbour GPUs themselves (PeerHalo) -- no exchange step, only a device-side barrier."""
         from .jbf import JointBilateralFilter
         self.plan = make_plan(width, height, radius, rank, world)
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device) if isinstance(device, int) else device
-        self.halo = HaloExchanger(self.plan, self.device, group)
+        self.peer_memory = bool(peer_memory) and world > 1
+        self.halo = PeerHalo(self.plan, self.device, group) if self.peer_memory else HaloExchanger(self.plan, self.device, group)
         p = self.plan
         self.jbf = JointBilateralFilter(width, p.ext_rows, spatial_sigma, color_sigma, depth_sigma, radius,
                                         max_batch=1, device=self.device.index)
@@ -181,6 +229,8 @@ class RowBandJBF:
         strips follow once the halos have landed.  Strips start on tile rows, so the result is bit-identical
         to the unsplit launch and to the single-GPU frame."""
         p = self.plan
+        if self.peer_memory:
+            return self.process_peer(barrier=exchange)
         edge = TILE_H * ((p.halo + TILE_H - 1) // TILE_H)          # seam strip height (tile multiple >= r + 2)
         top = edge if p.up else 0
         bot = edge if p.down else 0
@@ -207,4 +257,26 @@ class RowBandJBF:
             r0 = p.up + p.band_rows - 2 * R2
             self._presmooth(r0, p.ext_rows - r0, keep0=r0 + R2, keep1=p.ext_rows)
             self._filter(p.up + p.band_rows - bot_rows, bot_rows)
+        return self.out
+
+    def process_peer(self, barrier: bool = True, pointers=None) -> torch.Tensor:
+        """Peer-memory schedule: [barrier] -> pre-smooth (halo rows of BGR read from the neighbours) ->
+        filter (halo rows of depth read from the neighbours) -> [barrier].  `pointers` overrides the peer
+        pointers (single-GPU emulation in the tests): (depth_up, depth_dn, bgr_up, bgr_dn)."""
+        from . import _lib
+        p = self.plan
+        if pointers is None:
+            pointers = (self.halo.depth_up, self.halo.depth_dn, self.halo.bgr_up, self.halo.bgr_dn)
+        d_up, d_dn, b_up, b_dn = [None if not x else x for x in pointers]
+        if barrier:
+            self.halo.barrier()
+        L = _lib.lib()
+        h = self.jbf._h
+        band0, band1 = p.up, p.up + p.band_rows
+        _lib.check(L.jbf_presmooth_rows_p2p(h, self.halo.bgr_ext.data_ptr(), 3 * p.width, self.guide4.data_ptr(),
+                                            self.pitch * 4, p.ext_rows, band0, band1, b_up, b_dn))
+        _lib.check(L.jbf_filter_rows_p2p(h, self.halo.depth_ext.data_ptr(), self.guide4.data_ptr(), self.pitch * 4,
+                                         self.out.data_ptr(), p.ext_rows, p.up, p.band_rows, band0, band1, d_up, d_dn))
+        if barrier:
+            self.halo.barrier()
         return self.out

@@ -121,3 +121,43 @@ def test_row_bands_equal_whole_frame_bit_for_bit(w, h, radius, world, overlap):
         rb.halo.bgr_ext.copy_(c[p.y0 - p.up:p.y1 + p.down])
         got[p.y0:p.y1] = rb.process(exchange=False, overlap=overlap).cpu()   # overlap: interior first, seam strips after
     assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,radius,world", [(256, 192, 9, 2), (320, 256, 7, 4), (192, 400, 15, 3)])
+def test_peer_memory_halos_equal_whole_frame_bit_for_bit(w, h, radius, world):
+    """The peer-memory form (halo rows read from the neighbours' bands inside the kernels) emulated on one
+    GPU: every rank's arrays hold ONLY its band (halo rows poisoned with NaN / 255 to prove they are never
+    read) and the 'peer' pointers point into the other ranks' arrays on the same device."""
+    from kinectdepthmapenhancement_b200 import JointBilateralFilter
+    d, c = synth.rgbd_frame(w, h, seed=4, frame=radius)
+    os.environ["KDME_BIG_TILES"] = "1"
+    try:
+        full = JointBilateralFilter(w, h, window_radius=radius)
+    finally:
+        os.environ.pop("KDME_BIG_TILES", None)
+    full.Process(d.cuda(), c.cuda())
+    want = full.getFiltered_Device().cpu()
+    ranks = [shard.RowBandJBF(w, h, radius, r, world) for r in range(world)]
+    for rb in ranks:
+        p = rb.plan
+        rb.halo.depth_ext.fill_(float("nan"))
+        rb.halo.bgr_ext.fill_(255)
+        rb.depth_band.copy_(d[p.y0:p.y1])
+        rb.bgr_band.copy_(c[p.y0:p.y1])
+    got = torch.empty_like(want)
+    for r, rb in enumerate(ranks):
+        p = rb.plan
+        d_up = d_dn = b_up = b_dn = 0
+        if r > 0:
+            q = ranks[r - 1]
+            first = q.plan.up + q.plan.band_rows - p.up
+            d_up = q.halo.depth_ext.data_ptr() + first * w * 4
+            b_up = q.halo.bgr_ext.data_ptr() + first * w * 3
+        if r < world - 1:
+            q = ranks[r + 1]
+            d_dn = q.halo.depth_ext.data_ptr() + q.plan.up * w * 4
+            b_dn = q.halo.bgr_ext.data_ptr() + q.plan.up * w * 3
+        got[p.y0:p.y1] = rb.process_peer(barrier=False, pointers=(d_up, d_dn, b_up, b_dn)).cpu()
+    assert not torch.isnan(got).any()
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))

@@ -149,7 +149,8 @@ def band():
     n = int(os.environ.get("KDME_BAND_SIZE", "16384"))
     w = h = n
     r = 9
-    rb = shard.RowBandJBF(w, h, r, rank, world, device=local)
+    peer = os.environ.get("KDME_BAND_PEER", "0") == "1"
+    rb = shard.RowBandJBF(w, h, r, rank, world, device=local, peer_memory=peer)
     p = rb.plan
     # generate the band in slabs (position-keyed generator: any band on any rank)
     for y in range(p.y0, p.y1, 512):
@@ -178,7 +179,7 @@ def band():
     x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     x0.record()
     for _ in range(10):
-        rb.halo.exchange()
+        rb.halo.barrier() if rb.peer_memory else rb.halo.exchange()
     x1.record()
     torch.cuda.synchronize()
     xms = torch.tensor([x0.elapsed_time(x1) / 10], device="cuda", dtype=torch.float64)
@@ -189,7 +190,9 @@ def band():
         dist.all_reduce(checksum)
     if rank == 0:
         print(json.dumps({"workload": f"configs[4]: {w}x{h} synthetic RGB-D mosaic, r=9, row bands over {world} GPU(s), "
-                                      "halo exchange (r+2 rows of depth + BGR per direction) inside the timed step",
+                                      + ("halo rows read from peer memory inside the kernels (no exchange)" if rb.peer_memory else
+                                         "halo exchange (r+2 rows of depth + BGR per direction) inside the timed step"),
+                          "halo_mode": "peer_memory" if rb.peer_memory else "nccl_send_recv",
                           "n_gpus": world, "ms_per_frame": float(ms.item()), "mpixel_s": w * h / float(ms.item()) / 1e3,
                           "halo_exchange_ms": float(xms.item()), "halo_bytes_per_direction": p.halo_bytes_per_direction(),
                           "checksum": float(checksum.item()), "timing": "CUDA events, max over ranks"}))
