@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_const
     const float l2e = (float)kLog2e;
     const float sc0 = p.sigma_c;
     const float den0 = 2 * (sc0 * sc0);
+    const float inv_den0 = (sc0 != 0.0f) ? 1.0f / den0 : 0.f;   // sweep 1: one reciprocal per pixel, not a division per tap
 
     // accumulation origin: first sample in the window (keeps fp32 sums small)
     float d0 = 0.f;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_const
             const float cd = (float)__dp4a(ad, ad, 0u);
             float lg = sL[i * WS + j] + kWeightBias;
             if (sc0 != 0.0f) {
-                const float a = -cd / den0;
+                const float a = -cd * inv_den0;
                 if (a >= kZero) lg = fmaf(a, l2e, lg);
             }
             const float f = ex2_approx(lg);
@@ -154,7 +155,9 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_const
                 if (sigma != 0.0f) {
                     if (adaptive > sigma * 0.3f) sigma = adaptive; else sigma *= 0.3f;
                     const float dn = 2 * (sigma * sigma);
-                    const float a = -cd / dn;          // -0/0 = NaN when sigma^2 underflowed and cd == 0
+                    // fast reciprocal where it is safe; the exact quotient near underflow, where -0/0 = NaN
+                    // (sigma^2 underflowed to 0 and cd == 0) and cd/denormal must behave as in IEEE arithmetic
+                    const float a = (dn > 1.0e-30f) ? -cd * __frcp_rn(dn) : -cd / dn;
                     if (a != a) poisoned = true;       // expf(NaN) = NaN != 0 -> filter *= NaN
                     else if (a >= kZero) lg = fmaf(a, l2e, lg);
                 }
