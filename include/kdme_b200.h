@@ -65,6 +65,20 @@ int jbf_set_presmooth(jbf_handle *h, int ksize, float sigma_color, float sigma_s
  *   jbf_filtered_device(h). */
 int jbf_process(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step);
 
+/* Process followed by DimensionConvertor::projectiveToReal(float*, float3*) -- main.cpp:179 + :182,
+ * KinectDepthEnhancement.cpp:59-60, DimensionConvertor.h:34-48, DimensionConvertor.cpp:8-9 (cx, cy are the
+ * truncated principal point) -- as ONE launch pair: the filter's epilogue also writes the float3 cloud
+ * x = (u - cx)/fx * z, y = (cy - v)/fy * z, z (IEEE, un-fused, the functor's order) to xyz_dev
+ * [height][width][3].  The depth plane still lands in jbf_filtered_device(h). */
+int jbf_process_xyz(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step,
+                    float *xyz_dev, float fx, float fy, int cx, int cy);
+
+/* Numerical bookkeeping of the fast path (no reference counterpart): pixels whose window holds no sample
+ * near the pass-1 mean (a pixel between two surfaces) amplify the rounding of that mean beyond what fp32
+ * sums can absorb; the filter queues them and a second kernel re-evaluates them in fp64.  Returns how many
+ * were re-evaluated / dropped (queue full) since the previous call; synchronises the handle's stream. */
+int jbf_refine_stats(jbf_handle *h, unsigned long long *refined, unsigned long long *dropped);
+
 /* Same operator over n_frames independent frames stored back to back (frame
  * stride width*height elements / height*bgr_step bytes); out_dev receives
  * n_frames planes.  One launch pair for the whole batch (the B200-native form of

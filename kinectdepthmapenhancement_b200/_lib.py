@@ -45,6 +45,8 @@ SIGNATURES = {
     "jbf_destroy": (None, [_vp]),
     "jbf_set_presmooth": (_i, [_vp, _i, _f, _f]),
     "jbf_process": (_i, [_vp, _vp, _vp, _sz]),
+    "jbf_process_xyz": (_i, [_vp, _vp, _vp, _sz, _vp, _f, _f, _i, _i]),
+    "jbf_refine_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "jbf_process_batch": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "jbf_filter_guide4": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "jbf_presmooth": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),

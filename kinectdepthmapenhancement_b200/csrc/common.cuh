@@ -72,6 +72,14 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is
+// still running; grid_dependency_wait() blocks until the predecessor's memory is visible, and the
+// predecessor calls grid_launch_dependents() once its remaining work no longer gates the successor's
+// prologue.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: one issue slot, two lanes of fp32) ----------
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
@@ -85,6 +93,11 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {

@@ -44,18 +44,22 @@ struct JbfParams {
     long long depth_frame_stride;   // elements
     long long guide_frame_stride;   // words
     int guide_pitch;                // words per row
-    const float* ltab;           // [(2r+1)][LP]: log2(S_ij)+bias, or bias where S_ij == 0
-    const float* ltab_pairs;     // [(2r+1)][LPP][2]: {L[i][j], L[i][j-1]} for j = 1..2r (packed-math kernel)
+    const float* ltab;           // generic kernel: [(2r+1)][(2r+1)] log2(S_ij)+bias, or bias where S_ij == 0
+    const float* ltab_pairs;     // pass 2: [(2r+1)][LPP][2] = {L[i][j], L[i][j-1]}, j = 1..2r, bias kWeightBias
+    const float* ltab_pairs1;    // pass 1: same layout, bias `bias1` (0 whenever no pass-1 weight can flush)
+    const float* slut;           // the reference's raw fp32 spatial LUT [(2r+1)^2] (fp64 refinement path)
     float nkc;                   // -log2e / (2 sigma_c^2)
     float sq, inv_sq;            // depth scale sqrt(log2e/(2 sigma_d^2)) and inverse
     float e_thr;                 // sqrt(150): scaled |d - m| beyond which fp32 expf() == 0
+    float flag_scale;            // a pixel is refined in fp64 when den < wsum * flag_scale (ill-conditioned)
+    double kc, kd;               // 1/(2 sigma_c^2), 1/(2 sigma_d^2) (fp64 refinement path)
     int mode;                    // StageMode
     const float* depth_lo;       // upsample: low-res depth [hl][wl]
     int wl, hl;
     // row-band mode: the arrays hold `height` rows (band + halos); output rows are
-    // [y_off, y_off + out_rows) of them and `out` holds only those.  Tiles start at y_off, so a
-    // band whose first image row is a multiple of the tile height is tiled exactly like the
-    // whole image and the result is bit-identical.  Whole-image mode: y_off = 0, out_rows = height.
+    // [y_off, y_off + out_rows) of them and `out` holds only those.  Results do not depend on where
+    // tiles start vertically, so a band equals the same rows of the whole image bit for bit.
+    // Whole-image mode: y_off = 0, out_rows = height.
     int y_off, out_rows;
     // peer-memory halos (row bands over NVLink): rows [band0, band1) of the arrays are this rank's own;
     // when depth_up / depth_dn are non-null, rows above / below are read straight from the neighbour
@@ -64,6 +68,20 @@ struct JbfParams {
     const float* depth_up;
     const float* depth_dn;
     int band0, band1;
+    // fused back-projection epilogue (DimensionConvertor::projectiveToReal, DimensionConvertor.h:34-48):
+    // when xyz != nullptr the kernel also writes float3 {x, y, z} per pixel, [n][out_rows][W][3]
+    float* xyz;
+    float fx, fy;
+    int cx, cy;
+    int y_img0;                  // image row of array row 0 (bands), for the back-projection's v
+    // ill-conditioned pixels are queued here by the filter kernel and re-evaluated in fp64 by
+    // jbf_refine_kernel: q_count[0] = number pushed (may exceed q_capacity: the excess is dropped and
+    // counted), q_items = linear output indices (frame * out_rows * W + oy * W + x)
+    unsigned int* q_count;       // [0] pushed by this launch
+    unsigned int* q_count_prev;  // the previous launch's counter (two alternate): re-armed by this launch's filter kernel
+    unsigned int* q_items;
+    unsigned int q_capacity;
+    unsigned long long* stats;   // [0] += pixels refined in fp64, [1] += pixels dropped (queue full)
 };
 
 template <int R, int TW, int TH>
@@ -72,14 +90,13 @@ struct JbfTile {
     static constexpr int RP = (R + 3) & ~3;        // halo columns rounded up to a 16-byte multiple
     static constexpr int SP = TW + 2 * RP;         // staged row pitch (words)
     static constexpr int SH = TH + 2 * R;          // staged rows
-    static constexpr int LP = (WS + 3) & ~3;       // LUT row pitch
     static constexpr int NT = (TW / 4) * TH;       // threads per CTA
     static constexpr int NW = 2 * RP + 4;          // words fetched per row per thread
     static constexpr int C0 = RP - R;              // first used column of the fetched segment
     static constexpr int PLANE = ((SP * SH * 4 + 127) / 128) * 128;
     static constexpr int LPP = (WS - 1 + 1) & ~1;  // pairs per LUT row, padded to an even count (16-byte rows)
-    static constexpr int LBYTES = ((WS * (LPP > LP / 2 ? LPP * 2 : LP) * 4 + 127) / 128) * 128;
-    static constexpr int SMEM = 3 * PLANE + LBYTES + 128;
+    static constexpr int LBYTES = ((WS * LPP * 2 * 4 + 127) / 128) * 128;   // one paired table
+    static constexpr int SMEM = 3 * PLANE + 2 * LBYTES + 128;
 };
 
 // low-res sample index landing on high-res coordinate x, or -1:
@@ -91,21 +108,30 @@ __device__ __forceinline__ int upsample_site(int x, int W, int wl) {
     return ((int)(((2LL * xl + 1) * W) / (2LL * wl)) == x) ? xl : -1;
 }
 
-template <int R, int TW, int TH, int MINB, bool PACKED>
+// Knuth 2Sum on both lanes: a + b == s + t exactly; a <- s, lo += t.
+__device__ __forceinline__ void two_sum2(f32x2& a, const f32x2 b, f32x2& lo) {
+    const f32x2 s = add2(a, b);
+    const f32x2 bb = sub2(s, a);
+    const f32x2 t = add2(sub2(a, sub2(s, bb)), sub2(b, bb));
+    a = s;
+    lo = add2(lo, t);
+}
+
+template <int R, int TW, int TH, int MINB>
 __global__ void __launch_bounds__((TW / 4) * TH, MINB)
 jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_constant__ CUtensorMap tm_guide,
                 const JbfParams p) {
     using T = JbfTile<R, TW, TH>;
-    constexpr int WS = T::WS, RP = T::RP, SP = T::SP, SH = T::SH, LP = T::LP, NT = T::NT, NW = T::NW, C0 = T::C0;
+    constexpr int WS = T::WS, RP = T::RP, SP = T::SP, SH = T::SH, NT = T::NT, NW = T::NW, C0 = T::C0;
     constexpr int LPP = T::LPP;
 
     extern __shared__ __align__(128) uint8_t smem_fast[];
     float* sD = reinterpret_cast<float*>(smem_fast);
     uint32_t* sG = reinterpret_cast<uint32_t*>(smem_fast + T::PLANE);
     uint32_t* sM = reinterpret_cast<uint32_t*>(smem_fast + 2 * T::PLANE);
-    float* sL = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_fast + 3 * T::PLANE + T::LBYTES);
-    float* sRed = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE + T::LBYTES + 16);  // NT/32 <= 16 floats
+    float* sL1 = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE);
+    float* sL2 = reinterpret_cast<float*>(smem_fast + 3 * T::PLANE + T::LBYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_fast + 3 * T::PLANE + 2 * T::LBYTES);
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = p.y_off + blockIdx.y * TH, frame = blockIdx.z;
@@ -118,9 +144,24 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     // ---------------- stage A: raw depth + guide tile with halo -> shared memory
     if (mode == kStageTma) {
         if (tid == 0) {
+            tma_prefetch_desc(&tm_depth);
+            tma_prefetch_desc(&tm_guide);
             mbar_init(bar, 1);
             fence_mbar_init();
         }
+    }
+    // spatial LUT rows (log2 domain, paired for the packed math; host data, not produced by a prior kernel)
+    for (int idx = tid; idx < WS * LPP * 2; idx += NT) {
+        sL1[idx] = __ldg(p.ltab_pairs1 + idx);
+        sL2[idx] = __ldg(p.ltab_pairs + idx);
+    }
+    // programmatic dependent launch: everything above overlaps the tail of the pre-smooth kernel; the
+    // guide it writes is only read below this point (no-op when launched without the attribute)
+    grid_dependency_wait();
+    // re-arm the queue counter the PREVIOUS launch used (its refine kernel has completed: it precedes this
+    // kernel's stream predecessor, or is it); this launch pushes to the other one
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.q_count_prev = 0u;
+    if (mode == kStageTma) {
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(bar, 2u * SP * SH * 4u);
@@ -168,33 +209,14 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             sG[idx] = g;
         }
     }
-    // spatial LUT rows (log2 domain, bias folded in)
-    if (PACKED) {
-        for (int idx = tid; idx < WS * LPP * 2; idx += NT) sL[idx] = __ldg(p.ltab_pairs + idx);
-    } else {
-        for (int idx = tid; idx < WS * LP; idx += NT) sL[idx] = __ldg(p.ltab + idx);
-    }
     if (mode == kStageTma) mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---------------- stage B: validity, tile origin d_ref, scaled/shifted depth
-    float lmin = 3.0e38f;
+    // ---------------- stage B: validity word per staged sample; holes (and NaN) read as depth 0
     for (int idx = tid; idx < SP * SH; idx += NT) {
-        float d = sD[idx];
-        if (d > kValidDepth) lmin = fminf(lmin, d);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-    if ((tid & 31) == 0) sRed[tid >> 5] = lmin;
-    __syncthreads();
-    float dref = 3.0e38f;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) dref = fminf(dref, sRed[w]);
-    if (dref > 1.0e38f) dref = 0.f;
-    for (int idx = tid; idx < SP * SH; idx += NT) {
-        float d = sD[idx];
-        bool v = d > kValidDepth;
-        sD[idx] = v ? (d - dref) * p.sq : 0.f;
+        const float d = sD[idx];
+        const bool v = d > kValidDepth;
+        sD[idx] = v ? d : 0.f;
         sM[idx] = v ? kMagicValid : kMagicInvalid;
     }
     __syncthreads();
@@ -210,155 +232,81 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         const float4 d4 = *reinterpret_cast<const float4*>(sD + c);
         const uint4 m4 = *reinterpret_cast<const uint4*>(sM + c);
         gp[0] = g4.x; gp[1] = g4.y; gp[2] = g4.z; gp[3] = g4.w;
-        // per-thread accumulation origin: first valid own pixel (scaled, tile-relative)
+        // per-thread accumulation origin (raw millimetres): first valid own pixel, else the first valid
+        // sample of the thread's windows (own row first, then top to bottom) -- a function of the image
+        // around the thread only, so results do not depend on the tile a pixel falls in
         bool has = true;
         d0 = (m4.x == kMagicValid) ? d4.x
            : (m4.y == kMagicValid) ? d4.y
            : (m4.z == kMagicValid) ? d4.z
            : (m4.w == kMagicValid) ? d4.w : (has = false, 0.f);
-        // no valid own pixel (hole filling): borrow the origin of the nearest thread of the same
-        // tile row that has one (xor distances 1,2,4,8 within the TW/4 = 16 lanes of the row)
+        if (!has) {
+            // 16-byte reads of the validity plane, as the sweeps below do; the first valid column of the row
+            // segment [C0, C0 + WS + 3) wins
+#pragma unroll 1
+            for (int rr = 0; rr <= WS && !has; ++rr) {
+                const int rowoff = ((rr == 0) ? (ly + R) : (ly + rr - 1)) * SP + colbase;
+                int first = NW;
 #pragma unroll
-        for (int o = 1; o < TW / 4 && o < 32; o <<= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, d0, o);
-            const bool oh = __shfl_xor_sync(0xffffffffu, has ? 1 : 0, o) != 0;
-            if (!has && oh) { d0 = od; has = true; }
+                for (int v = NW / 4 - 1; v >= 0; --v) {
+                    const uint4 q4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
+                    if (4 * v + 3 >= C0 && 4 * v + 3 < C0 + WS + 3 && q4.w == kMagicValid) first = 4 * v + 3;
+                    if (4 * v + 2 >= C0 && 4 * v + 2 < C0 + WS + 3 && q4.z == kMagicValid) first = 4 * v + 2;
+                    if (4 * v + 1 >= C0 && 4 * v + 1 < C0 + WS + 3 && q4.y == kMagicValid) first = 4 * v + 1;
+                    if (4 * v + 0 >= C0 && 4 * v + 0 < C0 + WS + 3 && q4.x == kMagicValid) first = 4 * v + 0;
+                }
+                if (first < NW) { d0 = sD[rowoff + first]; has = true; }
+            }
         }
     }
+    // scaled units: X = d*sq - cO with cO = fl(d0*sq); fma(d, sq, -cO) rounds once, relative to the
+    // (small) difference; c_err = d0*sq - cO exactly, restored in the epilogue
+    const float sq = p.sq;
+    const float cO = __fmul_rn(d0, sq);
+    const float c_err = fmaf(d0, sq, -cO);
+    const float ncO = -cO;
     const float nkc = p.nkc;
-    float delta[4], num[4], den[4];
+    float delta[4], num[4], den[4], wsum[4];
     bool any[4];
 
-    if constexpr (!PACKED) {
+    // Pixels (0,1) and (2,3) of the thread share one tap column, so the FADD/FFMA of two taps issue as one
+    // FADD2/FFMA2 (scalar operands broadcast, LUT entries pre-paired as {L[j], L[j-1]}).  Per tap PAIR:
+    // 2 VABSDIFF4 + 2 IDP.4A + FADD2 + FFMA2 + 2 MUFU.EX2 + FFMA2 + FADD2 (pass 1), plus FADD2 + 2 FSETP +
+    // 2 predicated FFMA (pass 2).
+    const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+    const f32x2 nkc2 = pack2(nkc, nkc);
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int i = 0; i < WS; ++i) {
-        const int rowoff = (ly + i) * SP + colbase;
-        uint32_t gq[NW], mq[NW];
-        float dq[NW], L[LP];
-#pragma unroll
-        for (int v = 0; v < NW / 4; ++v) {
-            const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
-            const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
-            const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
-            gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
-            dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
-            mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
-        }
-#pragma unroll
-        for (int v = 0; v < LP / 4; ++v) {
-            const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
-            L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
-        }
-        // per-row partial sums: shorter fp32 accumulation chains (error grows with the chain length)
-        float racc[4] = {0.f, 0.f, 0.f, 0.f}, rws[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = C0; c < C0 + WS + 3; ++c) {
-            const float dsh = dq[c] - d0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = c - C0 - k;
-                if (j >= 0 && j < WS) {
-                    const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
-                    const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
-                    const float f = ex2_approx(fmaf(cdf, nkc, L[j]));
-                    racc[k] = fmaf(f, dsh, racc[k]);
-                    rws[k] += f;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { acc[k] += racc[k]; wsum[k] += rws[k]; }
+#define KDME_LOAD_ROW(SL)                                                                              \
+    const int rowoff = (ly + i) * SP + colbase;                                                        \
+    uint32_t gq[NW], mq[NW];                                                                           \
+    float dq[NW];                                                                                      \
+    f32x2 LPr[LPP];                                                                                    \
+    _Pragma("unroll") for (int v = 0; v < NW / 4; ++v) {                                               \
+        const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);                         \
+        const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);                       \
+        const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);                         \
+        gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;            \
+        dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;            \
+        mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;            \
+    }                                                                                                  \
+    _Pragma("unroll") for (int v = 0; v < LPP / 2; ++v) {                                              \
+        const float4 l4 = *reinterpret_cast<const float4*>(SL + (i * LPP + 2 * v) * 2);                \
+        LPr[2 * v] = pack2(l4.x, l4.y);                                                                \
+        LPr[2 * v + 1] = pack2(l4.z, l4.w);                                                            \
     }
 
-    // pass-1 weighted mean, in scaled tile-relative units
-    // the mean is kept as (d0, delta): e = (d - d0) - delta keeps full precision even when the tile
-    // spans metres of depth
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        any[k] = wsum[k] > 0.f;
-        delta[k] = any[k] ? (acc[k] / wsum[k]) : 0.f;
-    }
-
-    const float e_thr = p.e_thr;
-    for (int k = 0; k < 4; ++k) { num[k] = 0.f; den[k] = 0.f; }
-#pragma unroll 1
-    for (int i = 0; i < WS; ++i) {
-        const int rowoff = (ly + i) * SP + colbase;
-        uint32_t gq[NW], mq[NW];
-        float dq[NW], L[LP];
-#pragma unroll
-        for (int v = 0; v < NW / 4; ++v) {
-            const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
-            const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
-            const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
-            gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
-            dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
-            mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
-        }
-#pragma unroll
-        for (int v = 0; v < LP / 4; ++v) {
-            const float4 l4 = *reinterpret_cast<const float4*>(sL + i * LP + 4 * v);
-            L[4 * v] = l4.x; L[4 * v + 1] = l4.y; L[4 * v + 2] = l4.z; L[4 * v + 3] = l4.w;
-        }
-        float rnum[4] = {0.f, 0.f, 0.f, 0.f}, rden[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = C0; c < C0 + WS + 3; ++c) {
-            const float dsh = dq[c] - d0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = c - C0 - k;
-                if (j >= 0 && j < WS) {
-                    const uint32_t ad = __vabsdiffu4(gp[k], gq[c]);
-                    const float cdf = __uint_as_float(__dp4a(ad, ad, mq[c])) - 8388608.0f;
-                    float arg = fmaf(cdf, nkc, L[j]);
-                    const float e = dsh - delta[k];
-                    // fp32 expf(-(d-m)^2/(2 sd^2)) == 0  <=>  factor skipped (.cu:67-68)
-                    if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
-                    const float f = ex2_approx(arg);
-                    rnum[k] = fmaf(f, e, rnum[k]);
-                    rden[k] += f;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { num[k] += rnum[k]; den[k] += rden[k]; }
-    }
-
-    } else {
-        // ---- packed-math form: pixels (0,1) and (2,3) of the thread share one tap column, so the FADD/FFMA
-        // of two taps issue as one FADD2/FFMA2 (scalar operands broadcast, LUT entries pre-paired as
-        // {L[j], L[j-1]}).  Per tap PAIR: 2 VABSDIFF4 + 2 IDP.4A + FADD2 + FFMA2 + 2 MUFU.EX2 + FFMA2 + FADD2
-        // (pass 1), plus FADD2 + 2 FSETP + 2 predicated FFMA (pass 2).  Same arithmetic per lane as above.
-        const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
-        const f32x2 nkc2 = pack2(nkc, nkc);
+    // ---------------- pass 1: spatial x colour weighted mean (JointBilateralFilter.cu:16-40)
+    {
         f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull};
+        f32x2 accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};   // 2Sum low words of the row-level sums
 #pragma unroll 1
         for (int i = 0; i < WS; ++i) {
-            const int rowoff = (ly + i) * SP + colbase;
-            uint32_t gq[NW], mq[NW];
-            float dq[NW];
-            f32x2 LPr[LPP];
-#pragma unroll
-            for (int v = 0; v < NW / 4; ++v) {
-                const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
-                const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
-                const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
-                gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
-                dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
-                mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
-            }
-#pragma unroll
-            for (int v = 0; v < LPP / 2; ++v) {
-                const float4 l4 = *reinterpret_cast<const float4*>(sL + (i * LPP + 2 * v) * 2);
-                LPr[2 * v] = pack2(l4.x, l4.y);
-                LPr[2 * v + 1] = pack2(l4.z, l4.w);
-            }
+            KDME_LOAD_ROW(sL1)
+            // per-row partial sums, combined below without rounding error
             f32x2 raccP[2] = {0ull, 0ull}, rwsP[2] = {0ull, 0ull};
 #pragma unroll
             for (int c = C0; c < C0 + WS + 3; ++c) {
-                const float dsh = dq[c] - d0;
+                const float dsh = fmaf(dq[c], sq, ncO);
                 const f32x2 dsh2 = pack2(dsh, dsh);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
@@ -390,44 +338,41 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 }
             }
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) { accP[pr] = add2(accP[pr], raccP[pr]); wsP[pr] = add2(wsP[pr], rwsP[pr]); }
+            for (int pr = 0; pr < 2; ++pr) {
+                two_sum2(accP[pr], raccP[pr], accL[pr]);
+                two_sum2(wsP[pr], rwsP[pr], wsL[pr]);
+            }
         }
-        float acc[4], wsum[4];
+        float acc[4], accl[4], wsl[4];
         unpack2(accP[0], acc[0], acc[1]); unpack2(accP[1], acc[2], acc[3]);
         unpack2(wsP[0], wsum[0], wsum[1]); unpack2(wsP[1], wsum[2], wsum[3]);
+        unpack2(accL[0], accl[0], accl[1]); unpack2(accL[1], accl[2], accl[3]);
+        unpack2(wsL[0], wsl[0], wsl[1]); unpack2(wsL[1], wsl[2], wsl[3]);
+        // pass-1 weighted mean in scaled units relative to cO: (acc + accl) / (wsum + wsl), correctly
+        // rounded quotient of the compensated sums (one Newton-style residual step)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             any[k] = wsum[k] > 0.f;
-            delta[k] = any[k] ? (acc[k] / wsum[k]) : 0.f;
+            const float dh = acc[k] / wsum[k];
+            float res = fmaf(-dh, wsum[k], acc[k]);
+            res += accl[k];
+            res = fmaf(-dh, wsl[k], res);
+            delta[k] = any[k] ? (dh + res / wsum[k]) : 0.f;
         }
+    }
+
+    // ---------------- pass 2: range term centred on the pass-1 mean (JointBilateralFilter.cu:43-73)
+    {
         const f32x2 ndelP[2] = {pack2(-delta[0], -delta[1]), pack2(-delta[2], -delta[3])};
         const float e_thr = p.e_thr;
         f32x2 numP[2] = {0ull, 0ull}, denP[2] = {0ull, 0ull};
 #pragma unroll 1
         for (int i = 0; i < WS; ++i) {
-            const int rowoff = (ly + i) * SP + colbase;
-            uint32_t gq[NW], mq[NW];
-            float dq[NW];
-            f32x2 LPr[LPP];
-#pragma unroll
-            for (int v = 0; v < NW / 4; ++v) {
-                const uint4 g4 = *reinterpret_cast<const uint4*>(sG + rowoff + 4 * v);
-                const float4 d4 = *reinterpret_cast<const float4*>(sD + rowoff + 4 * v);
-                const uint4 m4 = *reinterpret_cast<const uint4*>(sM + rowoff + 4 * v);
-                gq[4 * v] = g4.x; gq[4 * v + 1] = g4.y; gq[4 * v + 2] = g4.z; gq[4 * v + 3] = g4.w;
-                dq[4 * v] = d4.x; dq[4 * v + 1] = d4.y; dq[4 * v + 2] = d4.z; dq[4 * v + 3] = d4.w;
-                mq[4 * v] = m4.x; mq[4 * v + 1] = m4.y; mq[4 * v + 2] = m4.z; mq[4 * v + 3] = m4.w;
-            }
-#pragma unroll
-            for (int v = 0; v < LPP / 2; ++v) {
-                const float4 l4 = *reinterpret_cast<const float4*>(sL + (i * LPP + 2 * v) * 2);
-                LPr[2 * v] = pack2(l4.x, l4.y);
-                LPr[2 * v + 1] = pack2(l4.z, l4.w);
-            }
+            KDME_LOAD_ROW(sL2)
             f32x2 rnumP[2] = {0ull, 0ull}, rdenP[2] = {0ull, 0ull};
 #pragma unroll
             for (int c = C0; c < C0 + WS + 3; ++c) {
-                const float dsh = dq[c] - d0;
+                const float dsh = fmaf(dq[c], sq, ncO);
                 const f32x2 dsh2 = pack2(dsh, dsh);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
@@ -473,19 +418,52 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
         unpack2(numP[0], num[0], num[1]); unpack2(numP[1], num[2], num[3]);
         unpack2(denP[0], den[0], den[1]); unpack2(denP[1], den[2], den[3]);
     }
+#undef KDME_LOAD_ROW
 
-    // ---------------- epilogue: back to millimetres, 16-byte store
+    // ---------------- epilogue: back to millimetres
     float o[4];
+    bool flag[4];
+    bool anyflag = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        // den > 0 whenever any tap is valid (weights are biased into the normal range)
-        const float r = ((delta[k] + num[k] / den[k]) + d0) * p.inv_sq;
-        o[k] = any[k] ? (dref + r) : 0.f;
+        // den > 0 whenever any tap is valid (pass-2 weights are biased into the normal range)
+        const float t = (delta[k] + num[k] / den[k]) - c_err;
+        o[k] = any[k] ? fmaf(t, p.inv_sq, d0) : 0.f;
+        // den / wsum = mean range weight of the window.  When it is tiny, no sample lies near the pass-1
+        // mean (a pixel between two surfaces): the output then amplifies the rounding of that mean by
+        // (distance / sigma_d)^2, beyond what fp32 sums can absorb -> such pixels are re-evaluated in fp64.
+        flag[k] = any[k] && !(den[k] >= wsum[k] * p.flag_scale);
+        anyflag |= flag[k];
     }
     const int gy = y0 + ly, gx = x0 + 4 * lx;
     const int oy = gy - p.y_off;
+    if (__any_sync(0xffffffffu, anyflag)) {
+        // queue the flagged pixels of this warp (one atomic per warp)
+        const int lane = tid & 31;
+        unsigned m[4];
+        int total = 0, before = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k] = __ballot_sync(0xffffffffu, flag[k] && oy < p.out_rows && gx + k < p.width);
+            before += __popc(m[k] & ((1u << lane) - 1u));
+            total += __popc(m[k]);
+        }
+        unsigned base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(p.q_count, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        // slots: lane-major (all flagged pixels of lane 0, then lane 1, ...)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((m[k] >> lane) & 1u) {
+                const unsigned slot = base + (unsigned)before;
+                ++before;
+                if (slot < p.q_capacity)
+                    p.q_items[slot] = (unsigned)(((long long)frame * p.out_rows + oy) * p.width + gx + k);
+            }
+    }
     if (oy < p.out_rows && gx < p.width) {
-        float* dst = p.out + (long long)frame * p.width * p.out_rows + (long long)oy * p.width + gx;
+        const long long pix = (long long)frame * p.width * p.out_rows + (long long)oy * p.width + gx;
+        float* dst = p.out + pix;
         if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
             stg_stream_f4(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
         } else {
@@ -493,6 +471,160 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             for (int k = 0; k < 4; ++k)
                 if (gx + k < p.width) dst[k] = o[k];
         }
+        if (p.xyz != nullptr) {
+            // DimensionConvertor::projectiveToReal (DimensionConvertor.h:34-48): x = (u - cx)/fx * z,
+            // y = (cy - v)/fy * z, IEEE division and un-fused ops in the reference functor's order
+            float v3[12];
+            const float py = __fdiv_rn(__fsub_rn((float)p.cy, (float)(p.y_img0 + gy)), p.fy);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float px = __fdiv_rn(__fsub_rn((float)(gx + k), (float)p.cx), p.fx);
+                v3[3 * k + 0] = __fmul_rn(px, o[k]);
+                v3[3 * k + 1] = __fmul_rn(py, o[k]);
+                v3[3 * k + 2] = o[k];
+            }
+            float* xdst = p.xyz + 3 * pix;
+            if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(xdst) & 15) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    stg_stream_f4(reinterpret_cast<float4*>(xdst) + q,
+                                  make_float4(v3[4 * q], v3[4 * q + 1], v3[4 * q + 2], v3[4 * q + 3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (gx + k < p.width) { xdst[3 * k] = v3[3 * k]; xdst[3 * k + 1] = v3[3 * k + 1]; xdst[3 * k + 2] = v3[3 * k + 2]; }
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------
+// fp64 refinement of the queued (ill-conditioned) pixels.  One warp per pixel: the taps of its window are
+// split across the 32 lanes and the four sums are combined with warp shuffles.  This is the reference
+// formula (JointBilateralFilter.cu:16-78) with exact exponentials, fp32 only where the reference's
+// skip-if-zero guards are decided.  Reads the frame from global memory (just filtered: L2-resident), so
+// it is independent of the filter kernel's tiling; the whole GPU shares the queue, so a frame whose
+// ill-conditioned pixels cluster in one place (a hole between two surfaces) costs no tail.
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+__device__ __forceinline__ float jbf_sample_depth(const JbfParams& p, int frame, int gx, int gy) {
+    if (p.mode == kStageUpsample) {
+        const int xl = upsample_site(gx, p.width, p.wl), yl = upsample_site(gy, p.height, p.hl);
+        return ((xl >= 0) & (yl >= 0)) ? __ldg(p.depth_lo + (long long)yl * p.wl + xl) : 0.f;
+    }
+    const float* row = p.depth + (long long)frame * p.depth_frame_stride + (long long)gy * p.width;
+    if (p.depth_up != nullptr && gy < p.band0) row = p.depth_up + (long long)gy * p.width;
+    else if (p.depth_dn != nullptr && gy >= p.band1) row = p.depth_dn + (long long)(gy - p.band1) * p.width;
+    return __ldg(row + gx);
+}
+
+// exp(-x) for x >= 0 in fp64 without the library's special-case handling: 2^(-x log2e) by Cody-Waite
+// reduction (n = nearest integer, |f| <= 0.5) and the degree-11 Taylor polynomial of e^(f ln2) (truncation
+// < 1e-14 relative), exponent attached by integer add.  Arguments beyond the double range return 0.
+__device__ __forceinline__ double exp_neg_f64(double x) {
+    const double t = -x * 1.4426950408889634;                 // log2 domain, <= 0
+    if (t < -1000.0) return 0.0;
+    const double kMagic = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
+    const double tn = t + kMagic;
+    const int n = __double2loint(tn);
+    const double f = (t - (tn - kMagic)) * 0.6931471805599453; // natural-log units, |f| <= 0.3466
+    double p = 2.505210838544172e-08;                          // 1/11!
+    p = fma(p, f, 2.755731922398589e-07);
+    p = fma(p, f, 2.755731922398589e-06);
+    p = fma(p, f, 2.48015873015873e-05);
+    p = fma(p, f, 1.984126984126984e-04);
+    p = fma(p, f, 1.388888888888889e-03);
+    p = fma(p, f, 8.333333333333333e-03);
+    p = fma(p, f, 4.166666666666666e-02);
+    p = fma(p, f, 1.666666666666667e-01);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// KMAX = taps per lane the instantiation can hold: (2r+1)^2 <= 32 * KMAX
+template <int KMAX>
+__global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, const int radius) {
+    grid_dependency_wait();   // the queue is complete only when the filter kernel has finished
+    const int lane = threadIdx.x & 31;
+    const unsigned pushed = *reinterpret_cast<volatile unsigned int*>(p.q_count);
+    const unsigned count = pushed < p.q_capacity ? pushed : p.q_capacity;
+    const int ws = 2 * radius + 1, ntap = ws * ws;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < count; item += nwarps) {
+        const unsigned idx = p.q_items[item];
+        const unsigned per_frame = (unsigned)p.out_rows * (unsigned)p.width;
+        const int frame = (int)(idx / per_frame);
+        const unsigned rem = idx - (unsigned)frame * per_frame;
+        const int oy = (int)(rem / (unsigned)p.width), x = (int)(rem - (unsigned)oy * (unsigned)p.width);
+        const int y = oy + p.y_off;
+        const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
+        const uint32_t gpix = __ldg(gsrc + (long long)y * p.guide_pitch + x);
+        // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight
+        double dl[KMAX], fl[KMAX];
+        double a = 0.0, wt = 0.0;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int t = lane + 32 * u;
+            dl[u] = 0.0;
+            fl[u] = 0.0;
+            if (t < ntap) {
+                const int i = t / ws, j = t - i * ws;
+                const int ty = y + i - radius, tx = x + j - radius;
+                if (tx >= 0 && tx < p.width && ty >= 0 && ty < p.height) {
+                    const float df = jbf_sample_depth(p, frame, tx, ty);
+                    if (df > kValidDepth) {
+                        const uint32_t ad = __vabsdiffu4(gpix, __ldg(gsrc + (long long)ty * p.guide_pitch + tx));
+                        const double cd = (double)__dp4a(ad, ad, 0u);
+                        double f = 1.0;
+                        const float s = __ldg(p.slut + t);
+                        if (s != 0.0f) f *= (double)s;
+                        f *= exp_neg_f64(cd * p.kc);
+                        dl[u] = (double)df;
+                        fl[u] = f;
+                        a += dl[u] * f;
+                        wt += f;
+                    }
+                }
+            }
+        }
+        a = warp_sum_f64(a);
+        wt = warp_sum_f64(wt);
+        float r = 0.f;
+        if (wt > 0.0) {
+            const double m = a / wt;
+            double num = 0.0, den = 0.0;
+#pragma unroll
+            for (int u = 0; u < KMAX; ++u) {
+                double f = fl[u];
+                const double e = dl[u] - m;
+                const double q = e * e * p.kd;
+                if (q <= kExpZeroArg) f *= exp_neg_f64(q);   // else fp32 expf() == 0: factor skipped (.cu:67-68)
+                num += dl[u] * f;
+                den += f;
+            }
+            num = warp_sum_f64(num);
+            den = warp_sum_f64(den);
+            r = (den == 0.0) ? 0.f : (float)(num / den);
+        }
+        if (lane == 0) {
+            p.out[idx] = r;
+            if (p.xyz != nullptr) {
+                const float px = __fdiv_rn(__fsub_rn((float)x, (float)p.cx), p.fx);
+                const float py = __fdiv_rn(__fsub_rn((float)p.cy, (float)(p.y_img0 + y)), p.fy);
+                float* xd = p.xyz + 3ll * idx;
+                xd[0] = __fmul_rn(px, r); xd[1] = __fmul_rn(py, r); xd[2] = r;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.stats != nullptr && pushed != 0u) {
+        atomicAdd(p.stats, (unsigned long long)count);
+        atomicAdd(p.stats + 1, (unsigned long long)(pushed - count));
     }
 }
 

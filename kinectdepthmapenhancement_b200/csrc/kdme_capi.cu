@@ -4,6 +4,8 @@
 // calcSpatialFilter, JointBilateralFilter.cpp:31-40), kernel selection, TMA
 // descriptor encoding, launch.  There is no CPU fallback: every entry point
 // either launches a CUDA kernel or returns an error.
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <climits>
 #include <cstdio>
@@ -98,14 +100,29 @@ struct jbf_handle {
     int guide_pitch = 0;             // words
     uint8_t* smooth_bgr = nullptr;   // packed copy for getSmoothImage_Device (lazy)
     float* ltab_dev = nullptr;       // fast layout [WS][LP]
-    float* ltab_pairs_dev = nullptr; // packed-math layout [WS][LPP][2] = {L[i][j], L[i][j-1]}, j = 1..WS-1
+    float* ltab_pairs_dev = nullptr; // packed-math layout [WS][LPP][2] = {L[i][j], L[i][j-1]}, j = 1..WS-1 (pass 2, bias 32)
+    float* ltab_pairs1_dev = nullptr;// same layout for pass 1, bias `bias1`
+    float* slut_dev = nullptr;       // the raw fp32 LUT of calcSpatialFilter [WS][WS] (fp64 refinement path)
+    unsigned long long* stats_dev = nullptr;  // [0] pixels refined in fp64, [1] dropped (queue full), since the last jbf_refine_stats
+    unsigned int* q_count_dev = nullptr;      // refinement queue (see JbfParams): two alternating counters
+    int q_cur = 0;
+    unsigned int* q_items_dev = nullptr;
+    size_t q_capacity = 0;
+    float bias1 = 0.f, flag_scale = 0.f;
+    double kc = 0, kd = 0;
     float* ltab_generic_dev = nullptr;  // [WS][WS]
     // derived
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
-    bool force_no_tma = false, force_big_tiles = false, scalar_math = false;
+    bool force_no_tma = false, force_big_tiles = false, no_refine = false;
+    int force_tile_h = 0;
     int last_variant = 0;
+    // TMA descriptors of the last fast launch, reused while (pointers, rows, frames, box) are unchanged
+    struct MapKey { const void* depth = nullptr; const void* guide = nullptr; int rows = 0, n = 0, gp = 0, bx = 0, by = 0; } map_key;
+    CUtensorMap map_depth, map_guide;
+    // fused back-projection (jbf_process_xyz): set for one launch
+    float* xyz_out = nullptr; float xyz_fx = 0, xyz_fy = 0; int xyz_cx = 0, xyz_cy = 0, xyz_yimg0 = 0;
     // host pipeline (jbf_process_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[kPipeDepth] = {}, ev_done[kPipeDepth] = {}, ev_free[kPipeDepth] = {};
@@ -143,16 +160,42 @@ static int build_tables(jbf_handle* h) {
             lf[(size_t)i * lp + j] = l;
             lg[(size_t)i * ws + j] = l;
         }
+    // pass 1 evaluates 2^(arg + bias1): with bias1 = 0 the heavy taps' arguments are rounded near 0
+    // (ulp ~1e-8) instead of near 32 (ulp 3.8e-6), which is what the pass-1 mean's accuracy needs.  The
+    // bias is only kept when some pass-1 weight could otherwise flush to zero under ex2.approx.ftz.
+    double lmin = 0.0;
+    for (size_t i = 0; i < lut.size(); i++)
+        if (lut[i] != 0.0f && std::isfinite(lut[i])) lmin = std::min(lmin, std::log2((double)lut[i]));
+    const double cmin = (h->sigma_c != 0.0f) ? -kLog2e * 3.0 * 255.0 * 255.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
+    h->bias1 = (lmin + cmin > -120.0) ? 0.f : kWeightBias;
     const int lpp = (ws - 1 + 1) & ~1;
-    std::vector<float> lpairs((size_t)ws * (lpp > 0 ? lpp : 1) * 2, 0.f);
+    std::vector<float> lpairs((size_t)ws * (lpp > 0 ? lpp : 1) * 2, 0.f), lpairs1(lpairs.size(), 0.f);
+    const float dbias = h->bias1 - kWeightBias;
     for (int i = 0; i < ws; i++)
         for (int j = 1; j < ws; j++) {
             lpairs[((size_t)i * lpp + (j - 1)) * 2 + 0] = lf[(size_t)i * lp + j];
             lpairs[((size_t)i * lpp + (j - 1)) * 2 + 1] = lf[(size_t)i * lp + j - 1];
         }
+    for (int i = 0; i < ws; i++)
+        for (int j = 0; j < ws; j++) {
+            const float s = lut[(size_t)i * ws + j];
+            const float l1 = (s != 0.0f && std::isfinite(s)) ? (float)(std::log2((double)s) + (double)h->bias1) : h->bias1;
+            if (j >= 1) lpairs1[((size_t)i * lpp + (j - 1)) * 2 + 0] = l1;
+            if (j + 1 < ws) lpairs1[((size_t)i * lpp + j) * 2 + 1] = l1;
+        }
+    (void)dbias;
     CK(cudaMalloc(&h->ltab_pairs_dev, lpairs.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->ltab_pairs_dev, lpairs.data(), lpairs.size() * sizeof(float), cudaMemcpyHostToDevice,
                        h->stream));
+    CK(cudaMalloc(&h->ltab_pairs1_dev, lpairs1.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->ltab_pairs1_dev, lpairs1.data(), lpairs1.size() * sizeof(float), cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaMalloc(&h->slut_dev, lut.size() * sizeof(float)));
+    CK(cudaMemcpyAsync(h->slut_dev, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMalloc(&h->stats_dev, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->stats_dev, 0, 2 * sizeof(unsigned long long), h->stream));
+    CK(cudaMalloc(&h->q_count_dev, 2 * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->q_count_dev, 0, 2 * sizeof(unsigned int), h->stream));
     CK(cudaMalloc(&h->ltab_dev, lf.size() * sizeof(float)));
     CK(cudaMalloc(&h->ltab_generic_dev, lg.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->ltab_dev, lf.data(), lf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -194,7 +237,12 @@ static int build_tables(jbf_handle* h) {
     if (getenv("KDME_FORCE_GENERIC")) h->fast = false;
     h->force_no_tma = getenv("KDME_NO_TMA") != nullptr;
     h->force_big_tiles = getenv("KDME_BIG_TILES") != nullptr;
-    h->scalar_math = getenv("KDME_SCALAR_MATH") != nullptr;
+    h->no_refine = getenv("KDME_NO_REFINE") != nullptr;
+    if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
+    h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
+    h->kd = h->use_depth ? 1.0 / (2.0 * (double)h->sigma_d * (double)h->sigma_d) : 0.0;
+    // refine in fp64 when the mean range weight den/wsum (biases removed) is below 2^-8
+    h->flag_scale = h->no_refine ? 0.f : (float)std::exp2((double)kWeightBias - (double)h->bias1 - 8.0);
     return KDME_OK;
 }
 
@@ -266,6 +314,11 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->smooth_bgr);
     cudaFree(h->ltab_dev);
     cudaFree(h->ltab_pairs_dev);
+    cudaFree(h->ltab_pairs1_dev);
+    cudaFree(h->slut_dev);
+    cudaFree(h->stats_dev);
+    cudaFree(h->q_count_dev);
+    cudaFree(h->q_items_dev);
     cudaFree(h->ltab_generic_dev);
     cudaFree(h->ps_space_dev);
     cudaFree(h->ps_color_dev);
@@ -325,31 +378,53 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
     return KDME_OK;
 }
 
-// One (radius, tile height) instantiation: encode the TMA maps for its box and launch.
-template <int R, int TH, bool PACKED>
-static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows) {
+// One (radius, tile height) instantiation: encode (or reuse) the TMA maps for its box and launch.
+template <int R, int TH>
+static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, bool pdl) {
     constexpr int TW = 64;
-    constexpr int MINB = (TH == 16) ? ((R <= 9) ? 3 : 2) : ((R <= 9) ? 6 : 4);  // 64x8: 600 CTAs of one Kinect frame must be co-resident (>= 5/SM)
     using T = JbfTile<R, TW, TH>;
-    auto kern = jbf_fast_kernel<R, TW, TH, MINB, PACKED>;
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    // resident CTAs per SM: by registers (<= 80 for r <= 9, <= 128 above: the row segment alone is
+    // 3 x (2r + 8) registers) and by shared memory
+    constexpr int kByRegs = (R <= 9 ? 65536 / 80 : 65536 / 128) / T::NT;
+    constexpr int kBySmem = (227 * 1024) / (T::SMEM + 1024);
+    constexpr int MINB = (kByRegs < kBySmem ? kByRegs : kBySmem) < 1 ? 1 : (kByRegs < kBySmem ? kByRegs : kBySmem);
+    auto kern = jbf_fast_kernel<R, TW, TH, MINB>;
+    static std::atomic<unsigned long long> attr_done{0};   // one bit per device
+    const unsigned long long bit = 1ull << (h->device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
-        attr_done[h->device & 63] = true;
+        attr_done.fetch_or(bit, std::memory_order_release);
     }
-    CUtensorMap tmd, tmg;
-    memset(&tmd, 0, sizeof(tmd)); memset(&tmg, 0, sizeof(tmg));
     if (want_tma) {
-        bool ok = encode_map(&tmd, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.depth, p.width, rows, p.n_frames,
-                             (long long)p.width * 4, (long long)p.width * rows * 4, T::SP, T::SH) &&
-                  encode_map(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.guide4, p.width, rows, p.n_frames,
-                             (long long)p.guide_pitch * 4, (long long)p.guide_pitch * rows * 4, T::SP, T::SH);
-        if (ok) p.mode = kStageTma;
+        jbf_handle::MapKey& k = h->map_key;
+        if (k.depth != p.depth || k.guide != p.guide4 || k.rows != rows || k.n != p.n_frames || k.gp != p.guide_pitch ||
+            k.bx != T::SP || k.by != T::SH) {
+            bool ok = encode_map(&h->map_depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.depth, p.width, rows, p.n_frames,
+                                 (long long)p.width * 4, (long long)p.width * rows * 4, T::SP, T::SH) &&
+                      encode_map(&h->map_guide, CU_TENSOR_MAP_DATA_TYPE_UINT32, p.guide4, p.width, rows, p.n_frames,
+                                 (long long)p.guide_pitch * 4, (long long)p.guide_pitch * rows * 4, T::SP, T::SH);
+            if (ok) {
+                k.depth = p.depth; k.guide = p.guide4; k.rows = rows; k.n = p.n_frames; k.gp = p.guide_pitch;
+                k.bx = T::SP; k.by = T::SH;
+            } else {
+                k = jbf_handle::MapKey();
+                want_tma = false;
+            }
+        }
+        if (want_tma) p.mode = kStageTma;
     }
-    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (PACKED ? 0x400 : 0);
-    dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
-    kern<<<grd, T::NT, T::SMEM, h->stream>>>(tmd, tmg, p);
-    CK(cudaGetLastError());
+    h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (TH == 4 ? 0x800 : 0) | 0x400;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
+    cfg.blockDim = dim3(T::NT);
+    cfg.dynamicSmemBytes = T::SMEM;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, h->map_depth, h->map_guide, p));
     return KDME_OK;
 }
 
@@ -368,7 +443,7 @@ static bool fast_radius_available(int r) {
 static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guide4, int guide_pitch, float* out,
                          int n, int mode, const float* depth_lo, int wl, int hl, int rows = -1, int y_off = 0,
                          int out_rows = -1, const float* depth_up = nullptr, const float* depth_dn = nullptr,
-                         int band0 = 0, int band1 = 0) {
+                         int band0 = 0, int band1 = 0, bool pdl = false) {
     JbfParams p;
     if (rows < 0) rows = h->height;
     if (out_rows < 0) out_rows = rows;
@@ -382,26 +457,78 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     p.guide_frame_stride = (long long)guide_pitch * rows;
     p.guide_pitch = guide_pitch;
     p.nkc = h->nkc; p.sq = h->sq; p.inv_sq = h->inv_sq; p.e_thr = h->e_thr;
+    p.flag_scale = h->flag_scale; p.kc = h->kc; p.kd = h->kd; p.slut = h->slut_dev; p.stats = h->stats_dev;
+    p.q_count = h->q_count_dev + h->q_cur; p.q_count_prev = h->q_count_dev + (h->q_cur ^ 1);
+    p.q_items = h->q_items_dev; p.q_capacity = (unsigned)h->q_capacity;
     p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
+    p.xyz = h->xyz_out; p.fx = h->xyz_fx; p.fy = h->xyz_fy; p.cx = h->xyz_cx; p.cy = h->xyz_cy; p.y_img0 = h->xyz_yimg0;
+    if (p.xyz && !h->fast) return fail(KDME_ENOTSUP, "the fused back-projection needs the fast kernel (default sigmas, r = 1..15)");
     if (h->fast) {
         p.ltab = h->ltab_dev;
         p.ltab_pairs = h->ltab_pairs_dev;
+        p.ltab_pairs1 = h->ltab_pairs1_dev;
         const bool want_tma = p.mode == kStagePlain && !h->force_no_tma && (h->width % 4 == 0) &&
                               (guide_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(depth) & 15) == 0) &&
                               ((reinterpret_cast<uintptr_t>(guide4) & 15) == 0);
-        // Small launches (a single Kinect frame is 300 tiles of 64x16 on 148 SMs) use 64x8 tiles: twice the
-        // CTAs, so the SMs are loaded evenly.  Whole-frame and band results do not depend on the choice of
-        // tile for parity, but bit-identity between band and whole-frame needs the same tile: bands pass
-        // y_off/out_rows and always use 64x16.
-        const long long ctas16 = (long long)((h->width + 63) / 64) * ((out_rows + 15) / 16) * n;
-        const bool small_tiles = (ctas16 < 4LL * 148 * 3) && (rows == out_rows) && !h->force_big_tiles;
+        // Tile height: the arithmetic of a pixel does not depend on the tile it falls in, so the choice is
+        // purely a scheduling one.  Large launches use 64x16 tiles (least halo per pixel); a launch of only
+        // a few waves (one Kinect frame is 300 such tiles on 148 SMs) is cut finer so that the most loaded
+        // SM holds as little more than the average as possible.
+        const int tx = (h->width + 63) / 64;
+        int best_th = 16;
+        double best_cost = 1e300;
+        const int cand[3] = {16, 8, 4};
+        for (int ci = 0; ci < 3; ++ci) {
+            const int th = cand[ci];
+            const long long ctas = (long long)tx * ((out_rows + th - 1) / th) * n;
+            const long long per_sm = (ctas + 147) / 148;
+            const double cost = (double)per_sm * (th + 0.06 * (th + 2 * h->radius) + 0.25);
+            if (cost < best_cost * 0.97) { best_cost = cost; best_th = th; }
+        }
+        if (h->force_big_tiles) best_th = 16;
+        if (h->force_tile_h == 16 || h->force_tile_h == 8 || h->force_tile_h == 4) best_th = h->force_tile_h;
+        // queue of ill-conditioned pixels: a quarter of the launch's pixels (at least 64 K entries); pixels
+        // beyond it keep their fp32 value and are counted (jbf_refine_stats)
+        const unsigned long long px = (unsigned long long)h->width * out_rows * n;
+        if (px > 0xFFFFFFFFull) return fail(KDME_ENOTSUP, "more than 2^32 pixels in one launch");
+        size_t want = (size_t)std::min<unsigned long long>(std::max<unsigned long long>(px / 4, 65536ull), px);
+        if (h->flag_scale > 0.f && want > h->q_capacity) {
+            CK(cudaStreamSynchronize(h->stream));
+            cudaFree(h->q_items_dev);
+            h->q_items_dev = nullptr; h->q_capacity = 0;
+            CK(cudaMalloc(&h->q_items_dev, want * sizeof(unsigned int)));
+            h->q_capacity = want;
+        }
+        p.q_items = h->q_items_dev; p.q_capacity = (unsigned)h->q_capacity;
+        int rc = KDME_ENOTSUP;
         switch (h->radius) {
-#define X(R) case R: return h->scalar_math ? (small_tiles ? launch_fast_rt<R, 8, false>(h, p, want_tma, rows) : launch_fast_rt<R, 16, false>(h, p, want_tma, rows)) \
-                                           : (small_tiles ? launch_fast_rt<R, 8, true>(h, p, want_tma, rows) : launch_fast_rt<R, 16, true>(h, p, want_tma, rows));
+#define X(R) case R: rc = best_th == 16 ? launch_fast_rt<R, 16>(h, p, want_tma, rows, pdl)                     \
+                        : best_th == 8 ? launch_fast_rt<R, 8>(h, p, want_tma, rows, pdl)                       \
+                                       : launch_fast_rt<R, 4>(h, p, want_tma, rows, pdl); break;
             KDME_FAST_RADII(X)
 #undef X
+            default: return fail(KDME_ENOTSUP, "no fast kernel for this radius");
         }
-        return fail(KDME_ENOTSUP, "no fast kernel for this radius");
+        if (rc != KDME_OK) return rc;
+        h->q_cur ^= 1;
+        if (h->flag_scale > 0.f) {
+            // fp64 re-evaluation of the queued pixels; launched with programmatic stream serialisation so its
+            // launch latency hides behind the filter (it waits for the filter's completion on the device)
+            if (p.mode == kStageTma) p.mode = kStagePlain;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(148 * 4);
+            cfg.blockDim = dim3(128);
+            cfg.stream = h->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (h->radius <= 7) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<8>, p, h->radius));
+            else if (h->radius <= 10) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<16>, p, h->radius));
+            else CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<31>, p, h->radius));
+        }
+        return KDME_OK;
     }
     // generic path
     JbfGenericParams gp;
@@ -412,10 +539,11 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     constexpr int TW = 32, TH = 8;
     const int SP = TW + 2 * h->radius, SH = TH + 2 * h->radius, ws = 2 * h->radius + 1;
     size_t smem = (size_t)SP * SH * 8 + (size_t)ws * ws * 4;
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    static std::atomic<unsigned long long> attr_done{0};
+    const unsigned long long bit = 1ull << (h->device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
         CK(cudaFuncSetAttribute(jbf_generic_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_done[h->device & 63] = true;
+        attr_done.fetch_or(bit, std::memory_order_release);
     }
     dim3 grd((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, n);
     jbf_generic_kernel<TW, TH><<<grd, TW * TH, smem, h->stream>>>(gp);
@@ -515,7 +643,7 @@ extern "C" int jbf_process_batch(jbf_handle* h, const float* depth_dev, const ui
         int rc = launch_presmooth(h, bgr_dev + (size_t)f0 * bgr_step * h->height, bgr_step, h->guide4, h->guide_pitch, n);
         if (rc != KDME_OK) return rc;
         rc = launch_filter(h, depth_dev + (size_t)f0 * plane, h->guide4, h->guide_pitch, out_dev + (size_t)f0 * plane, n,
-                           kStagePlain, nullptr, 0, 0);
+                           kStagePlain, nullptr, 0, 0, -1, 0, -1, nullptr, nullptr, 0, 0, /*pdl=*/true);
         if (rc != KDME_OK) return rc;
     }
     return KDME_OK;
@@ -526,6 +654,32 @@ extern "C" int jbf_process(jbf_handle* h, const float* depth_dev, const uint8_t*
     return jbf_process_batch(h, depth_dev, bgr_dev, bgr_step, h->filtered_dev, 1);
 }
 
+// Process + DimensionConvertor::projectiveToReal in one launch pair (main.cpp:179 + :182,
+// KinectDepthEnhancement.cpp:59-60): the filter's epilogue writes the float3 cloud beside the depth plane.
+extern "C" int jbf_process_xyz(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step,
+                               float* xyz_dev, float fx, float fy, int cx, int cy) {
+    if (!h || !depth_dev || !bgr_dev || !xyz_dev) return fail(KDME_EINVAL, "jbf_process_xyz: NULL argument");
+    if (!(fx != 0.f) || !(fy != 0.f)) return fail(KDME_EINVAL, "jbf_process_xyz: focal lengths must be non-zero");
+    h->xyz_out = xyz_dev; h->xyz_fx = fx; h->xyz_fy = fy; h->xyz_cx = cx; h->xyz_cy = cy; h->xyz_yimg0 = 0;
+    const int rc = jbf_process_batch(h, depth_dev, bgr_dev, bgr_step, h->filtered_dev, 1);
+    h->xyz_out = nullptr;
+    return rc;
+}
+
+// Pixels re-evaluated in fp64 (ill-conditioned: no sample near the pass-1 mean) and pixels dropped because
+// the queue was full, since the previous call.  Synchronises the handle's stream.
+extern "C" int jbf_refine_stats(jbf_handle* h, unsigned long long* refined, unsigned long long* dropped) {
+    if (!h) return fail(KDME_EINVAL, "jbf_refine_stats: NULL handle");
+    DeviceGuard g(h->device);
+    unsigned long long v[2] = {0, 0};
+    CK(cudaMemcpyAsync(v, h->stats_dev, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(h->stats_dev, 0, sizeof(v), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (refined) *refined = v[0];
+    if (dropped) *dropped = v[1];
+    return KDME_OK;
+}
+
 extern "C" int jbf_upsample(jbf_handle* h, const float* depth_lo_dev, int wl, int hl, const uint8_t* bgr_hi_dev,
                             size_t bgr_step, float* out_hi_dev) {
     if (!h || !depth_lo_dev || !bgr_hi_dev || !out_hi_dev) return fail(KDME_EINVAL, "jbf_upsample: NULL argument");
@@ -534,7 +688,8 @@ extern "C" int jbf_upsample(jbf_handle* h, const float* depth_lo_dev, int wl, in
     DeviceGuard g(h->device);
     int rc = launch_presmooth(h, bgr_hi_dev, bgr_step, h->guide4, h->guide_pitch, 1);
     if (rc != KDME_OK) return rc;
-    return launch_filter(h, nullptr, h->guide4, h->guide_pitch, out_hi_dev, 1, kStageUpsample, depth_lo_dev, wl, hl);
+    return launch_filter(h, nullptr, h->guide4, h->guide_pitch, out_hi_dev, 1, kStageUpsample, depth_lo_dev, wl, hl, -1, 0, -1,
+                         nullptr, nullptr, 0, 0, /*pdl=*/true);
 }
 
 // Host pipeline: kPipeDepth device slots of pipe_chunk frames each; H2D, compute and D2H run on three
@@ -591,7 +746,8 @@ extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const ui
         if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));  // slot output drained
         rc = launch_presmooth(h, h->pipe_bgr[b], bgr_step, h->guide4, h->guide_pitch, n);
         if (rc != KDME_OK) return rc;
-        rc = launch_filter(h, h->pipe_depth[b], h->guide4, h->guide_pitch, h->pipe_out[b], n, kStagePlain, nullptr, 0, 0);
+        rc = launch_filter(h, h->pipe_depth[b], h->guide4, h->guide_pitch, h->pipe_out[b], n, kStagePlain, nullptr, 0, 0, -1, 0,
+                           -1, nullptr, nullptr, 0, 0, /*pdl=*/true);
         if (rc != KDME_OK) return rc;
         CK(cudaEventRecord(h->ev_done[b], h->stream));
         CK(cudaStreamWaitEvent(h->s_d2h, h->ev_done[b], 0));
@@ -641,7 +797,7 @@ extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
     return h->smooth_bgr;
 }
 
-extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x700)) : -1; }
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0xF00)) : -1; }
 
 // ------------------------------------------------------------------ MRF (next row f1)
 extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,

@@ -53,6 +53,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParams p) {
+    grid_launch_dependents();   // PDL: the filter's prologue (LUTs, descriptors, barrier) may start now
     constexpr int NT = TW * TH;
     constexpr int RMAX = kPsMaxK / 2;
     constexpr int SPM = TW + 2 * RMAX, SHM = TH + 2 * RMAX;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
 // VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
 template <int TW, int TH>
 __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const PresmoothParams p) {
+    grid_launch_dependents();   // PDL: the filter's prologue (LUTs, descriptors, barrier) may start now
     constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
     constexpr int XO = 4 - R;                                               // first used column of a staged row
     __shared__ __align__(16) float sB[SP * SH];

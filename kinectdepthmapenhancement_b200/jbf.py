@@ -95,6 +95,32 @@ class JointBilateralFilter:
         self._keep = (depth_device, color_image)
         _lib.check(_lib.lib().jbf_process(self._h, _ptr(depth_device), _ptr(color_image), 3 * self.width))
 
+    def process_xyz(self, depth_device: torch.Tensor, color_image: torch.Tensor, fx: float, fy: float, cx: int,
+                    cy: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Process + DimensionConvertor::projectiveToReal fused (main.cpp:179 + :182): returns the float3
+        cloud [H, W, 3]; the depth plane is in getFiltered_Device() as after Process."""
+        _check_cuda(depth_device, torch.float32, "depth_device", self.device)
+        _check_cuda(color_image, torch.uint8, "color_image", self.device)
+        if tuple(depth_device.shape) != (self.height, self.width):
+            raise ValueError(f"depth must be [{self.height}, {self.width}]")
+        if tuple(color_image.shape) != (self.height, self.width, 3):
+            raise ValueError(f"color image must be [{self.height}, {self.width}, 3]")
+        if out is None:
+            out = torch.empty((self.height, self.width, 3), dtype=torch.float32, device=self.device)
+        _check_cuda(out, torch.float32, "out", self.device)
+        if tuple(out.shape) != (self.height, self.width, 3):
+            raise ValueError(f"out must be [{self.height}, {self.width}, 3]")
+        self._keep = (depth_device, color_image)
+        _lib.check(_lib.lib().jbf_process_xyz(self._h, _ptr(depth_device), _ptr(color_image), 3 * self.width,
+                                              _ptr(out), float(fx), float(fy), int(cx), int(cy)))
+        return out
+
+    def refine_stats(self) -> tuple[int, int]:
+        """(pixels re-evaluated in fp64, pixels dropped because the queue was full) since the last call."""
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        _lib.check(_lib.lib().jbf_refine_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def getFiltered_Device(self) -> torch.Tensor:
         """float* getFiltered_Device() const -- JointBilateralFilter.cpp:41-43 (borrowed view)."""
         ptr = _lib.lib().jbf_filtered_device(self._h)

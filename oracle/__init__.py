@@ -180,6 +180,47 @@ def jbf_envelope(depth, guide, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=J
     return o, band, mean
 
 
+def guard_active_mask(depth, mean64, window, sigma_d, margin_mm=1.0):
+    """Pixels whose window holds a valid tap at or beyond the fp32 expf() underflow distance from the
+    pass-1 mean, where the skip-if-zero guard (JointBilateralFilter.cu:67-68) gives the tap FULL weight.
+    There the output is a discontinuous, ill-conditioned function of the pass-1 mean."""
+    depth = _f32(depth)
+    h, w = depth.shape
+    r = window // 2
+    thr = np.sqrt(103.97207708399179 * 2.0 * sigma_d * sigma_d)
+    dp = np.pad(depth, r)
+    act = np.zeros((h, w), bool)
+    if not sigma_d > 0:
+        return act
+    for i in range(window):
+        for j in range(window):
+            dq = dp[i:i + h, j:j + w]
+            act |= (dq > 50) & (np.abs(dq - mean64) > thr - margin_mm)
+    return act
+
+
+def parity_block(out, depth, guide, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_C,
+                 sigma_d=JBF_SIGMA_D, threads=0):
+    """Parity figures of a filtered frame `out` against the fp64 evaluation of the reference formula, as
+    reported by bench.py / smoke() and asserted by tests/test_gpu_jbf.py (same definitions): mask
+    mismatches, max |err| on guard-inactive ("regular") pixels, max |err| and count on guard-active pixels."""
+    o64, mean = jbf(depth, guide, window, sigma_s, sigma_c, sigma_d, "f64", threads, return_mean=True)
+    act = guard_active_mask(depth, mean, window, sigma_d)
+    err = np.abs(np.asarray(out, np.float64) - o64.astype(np.float64))
+    reg = np.where(act, 0.0, err)
+    yr, xr = np.unravel_index(np.argmax(reg), reg.shape)
+    ea = np.where(act, err, 0.0)
+    ya, xa = np.unravel_index(np.argmax(ea), ea.shape)
+    return {
+        "mask_mismatches": int(np.count_nonzero((np.asarray(out) > 0) != (o64 > 0))),
+        "nan": int(np.count_nonzero(np.isnan(out))),
+        "max_abs_regular_mm": float(reg.max()), "worst_regular_yx": [int(yr), int(xr)],
+        "max_abs_active_mm": float(ea.max()), "worst_active_yx": [int(ya), int(xa)],
+        "n_active": int(act.sum()), "n_active_beyond_1e-3": int((act & (err > 1e-3)).sum()),
+        "frac_within_1e-3": float((err <= 1e-3).mean()), "pixels": int(err.size),
+    }
+
+
 def jbf_process(depth, bgr, window=JBF_WINDOW, sigma_s=JBF_SIGMA_S, sigma_c=JBF_SIGMA_C,
                 sigma_d=JBF_SIGMA_D, precision="f32", threads=0):
     """JointBilateralFilter::Process (JointBilateralFilter.cu:283-290): pre-smooth then filter."""

@@ -46,16 +46,6 @@ def synth_np(w, h, seed=1234, frame=0, **kw):
 
 
 def rule_active_mask(depth, mean64, window, sigma_d, margin_mm=1.0):
-    """Pixels whose window holds a valid tap at or beyond the fp32 expf() underflow distance
-    from the pass-1 mean (JointBilateralFilter.cu:67-68 skip-if-zero guard).  There the output
-    is a discontinuous, ill-conditioned function of the pass-1 mean ('Tolerance')."""
-    h, w = depth.shape
-    r = window // 2
-    thr = np.sqrt(103.97207708399179 * 2.0 * sigma_d * sigma_d)
-    dp = np.pad(depth, r)
-    act = np.zeros((h, w), bool)
-    for i in range(window):
-        for j in range(window):
-            dq = dp[i:i + h, j:j + w]
-            act |= (dq > 50) & (np.abs(dq - mean64) > thr - margin_mm)
-    return act
+    """See oracle.guard_active_mask (the definition bench.py's parity block uses too)."""
+    import oracle
+    return oracle.guard_active_mask(depth, mean64, window, sigma_d, margin_mm)

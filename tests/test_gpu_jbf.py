@@ -3,18 +3,16 @@
 Tolerance (north_star): valid/hole mask and output indexing bit-exact; filtered depth within
 1e-3 mm of the fp64 evaluation of the reference formula.  Written out (check_against_f64):
 
-    |kernel - oracle_f64| <= 1e-3 mm + envelope + 0.05 mm * [skip guard active]
+    |kernel - oracle_f64| <= 1e-3 mm          on EVERY pixel where the skip-if-zero guard is inactive
 
-envelope = how far the fp64 oracle's own output moves when its pass-1 mean is displaced by +-2
-fp32 ulps (~5e-4 mm at 3 m).  The reference stores that mean in a float
-(JointBilateralFilter.cu:16,40), so outputs inside the envelope are all faithful evaluations of
-its formula; at depth edges the output is up to ~100x as sensitive to the mean as elsewhere.
-"Skip guard active" = the window holds a valid tap at or beyond the fp32 expf() underflow
-distance (288.4 mm at sigma_d = 20) from the pass-1 mean, where JointBilateralFilter.cu:67-68
-gives the tap FULL weight; the output then mixes surfaces > 288 mm apart and a tap within
-round-off of the cut-off flips discontinuously (<= 1e-5 of the pixels may do so).  On top of the
-bound the kernel must be within 1e-3 mm on >= 98 % of pixels (or, on frames made mostly of depth
-edges, at least as often as the reference's own fp32 arithmetic is).
+flat, no conditioning term.  "Skip guard active" = the window holds a valid tap at or beyond the
+fp32 expf() underflow distance (288.4 mm at sigma_d = 20) from the pass-1 mean, where
+JointBilateralFilter.cu:67-68 gives the tap FULL weight: the output then mixes surfaces > 288 mm
+apart and is a discontinuous function of the pass-1 mean (a tap within round-off of the cut-off
+flips between ~0 and full weight).  Guard-active pixels are not absorbed into a looser bound: their
+count, worst error and coordinates are printed, every one of them must still lie within 0.05 mm +
+the fp64 formula's own sensitivity to +-2 fp32 ulps of its mean, and at most 1e-5 of a frame's pixels
+(the cut-off flips) may exceed that.
 """
 import os
 
@@ -63,30 +61,38 @@ def gpu_filter(depth, guide3, radius, ss=70.0, sc=50.0, sd=20.0, env=None):
     return out[0].cpu().numpy(), f.kernel_variant
 
 
-def check_against_f64(out, depth, guide3, ws, ss, sc, sd, label=""):
-    """Mask bit-exact; |out - fp64 oracle| <= 1e-3 mm + envelope(+-2 fp32 ulps of the pass-1 mean)
-    (+ 0.05 mm where the skip-if-zero guard is active).  See the module docstring and DESIGN.md."""
+def parity_figures(out, depth, guide3, ws, ss, sc, sd):
+    """The parity block bench.py and smoke() report (same definitions as the asserts below)."""
     o64, band, m64 = oracle.jbf_envelope(depth, guide3, ws, ss, sc, sd)
+    err = np.abs(out.astype(np.float64) - o64.astype(np.float64))
+    act = rule_active_mask(depth, m64, ws, sd) if sd > 0 else np.zeros(depth.shape, bool)
+    return o64, band, err, act
+
+
+def check_against_f64(out, depth, guide3, ws, ss, sc, sd, label=""):
+    """Mask bit-exact; |out - fp64 oracle| <= 1e-3 mm flat on every guard-inactive pixel; guard-active
+    pixels listed and sanity-bounded.  See the module docstring and DESIGN.md."""
+    o64, band, err, act = parity_figures(out, depth, guide3, ws, ss, sc, sd)
     o32 = oracle.jbf(depth, guide3, ws, ss, sc, sd, precision="f32")
     assert not np.isnan(out).any()
     assert np.array_equal(out > 0, o64 > 0), "valid/hole mask differs from the oracle"
     assert np.array_equal(out == 0, o64 == 0)
-    err = np.abs(out.astype(np.float64) - o64.astype(np.float64))
     e32 = np.abs(o32.astype(np.float64) - o64.astype(np.float64))
-    act = rule_active_mask(depth, m64, ws, sd) if sd > 0 else np.zeros(depth.shape, bool)
-    tol = TOL_MM + band + TOL_ACTIVE_MM * act
-    viol = err > tol
-    # a tap within fp32 round-off of the 288.4 mm cut-off flips between ~0 and FULL weight: explained
-    # outliers, allowed only on guard-active pixels and only a handful per frame
-    allowed = max(2, int(1e-5 * err.size))
+    reg = np.where(act, 0.0, err)
+    yr, xr = np.unravel_index(np.argmax(reg), reg.shape)
+    ea = np.where(act, err, 0.0)
+    ya, xa = np.unravel_index(np.argmax(ea), ea.shape)
+    out_act = act & (err > TOL_MM)
     frac = float((err <= TOL_MM).mean())
     frac32 = float((e32 <= TOL_MM).mean())
-    print(f"\n{label} ws={ws}: within 1e-3 mm: kernel {frac * 100:.3f}% (reference-order fp32 {frac32 * 100:.3f}%), "
-          f"max regular {err[~act].max(initial=0):.2e}, max active {err[act].max(initial=0):.2e}, "
-          f"active {act.mean() * 100:.1f}%, violations {int(viol.sum())} (allowed {allowed})")
-    assert viol.sum() <= allowed, f"{int(viol.sum())} pixels outside tolerance, worst excess {(err - tol).max():.4f} mm"
-    assert not (viol & ~act).any(), "a regular (well-conditioned) pixel is outside tolerance"
-    assert frac >= min(0.98, frac32) - 1e-4, "kernel must be within 1e-3 mm on >= 98 % of pixels, or at least as often as the reference's own fp32"
+    print(f"\n{label} ws={ws}: regular max {reg.max():.2e} mm at (y={yr}, x={xr}); guard-active {int(act.sum())} px "
+          f"({act.mean() * 100:.1f}%), of which {int(out_act.sum())} beyond 1e-3 mm, worst {ea.max():.2e} mm at "
+          f"(y={ya}, x={xa}); within 1e-3 mm overall: kernel {frac * 100:.4f}% (reference-order fp32 {frac32 * 100:.3f}%)")
+    assert reg.max() <= TOL_MM, f"guard-inactive pixel (y={yr}, x={xr}) off by {reg.max():.3e} mm (> 1e-3 mm flat)"
+    # sanity bound on the ill-conditioned guard-active pixels (listed above, never hidden)
+    viol = act & (err > TOL_MM + band + TOL_ACTIVE_MM)
+    allowed = max(2, int(1e-5 * err.size))
+    assert viol.sum() <= allowed, f"{int(viol.sum())} guard-active pixels beyond the sanity bound"
     return err, act
 
 
@@ -101,7 +107,7 @@ def test_filter_matches_f64_oracle_tma_path(w, h, radius):
     check_against_f64(out, depth, guide, 2 * radius + 1, 70.0, 50.0, 20.0, f"{w}x{h} variant=0x{variant:x}")
     # the other tile shape (64x16 instead of the 64x8 picked for small launches) must pass the same bound
     out_big, vbig = gpu_filter(depth, guide, radius, env={"KDME_BIG_TILES": "1"})
-    assert not (vbig & 0x200)
+    assert not (vbig & 0xA00)
     check_against_f64(out_big, depth, guide, 2 * radius + 1, 70.0, 50.0, 20.0, f"{w}x{h} variant=0x{vbig:x}")
 
 
@@ -146,15 +152,36 @@ def test_fuzz_small_frames(seed):
                       f"fuzz {w}x{h} r={radius} ss={ss} sc={sc} sd={sd} holes={hole} variant=0x{variant:x}")
 
 
-def test_packed_and_scalar_math_bit_identical():
-    """FFMA2/FADD2 (packed fp32x2) compute the same bits per lane as the scalar FADD/FFMA form."""
+def test_result_independent_of_tile_height():
+    """A pixel's arithmetic depends only on the image around it, not on the tile it falls in: 64x16, 64x8
+    and 64x4 tiles give the same bits (this is what makes row bands equal the whole frame)."""
     depth, bgr = synth_np(320, 240, seed=8, frame=1)
     guide = oracle.presmooth(bgr)
     for r in (2, 7, 10):
-        a, va = gpu_filter(depth, guide, r)
-        b, vb = gpu_filter(depth, guide, r, env={"KDME_SCALAR_MATH": "1"})
-        assert (va & 0x400) and not (vb & 0x400)
+        a, va = gpu_filter(depth, guide, r, env={"KDME_TILE_H": "16"})
+        b, vb = gpu_filter(depth, guide, r, env={"KDME_TILE_H": "8"})
+        c, vc = gpu_filter(depth, guide, r, env={"KDME_TILE_H": "4"})
+        assert not (va & 0xA00) and (vb & 0x200) and (vc & 0x800)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+def test_fp64_refinement_of_ill_conditioned_pixels():
+    """Pixels between two surfaces (no sample near the pass-1 mean) are re-evaluated in fp64 by the whole
+    warp; with the refinement disabled the same frame must differ ONLY there, and the refined values are
+    the ones within tolerance."""
+    depth, bgr = synth_np(320, 240, seed=8, frame=0)
+    guide = oracle.presmooth(bgr)
+    a, _ = gpu_filter(depth, guide, 7)
+    b, _ = gpu_filter(depth, guide, 7, env={"KDME_NO_REFINE": "1"})
+    o64, band, err_a, act = parity_figures(a, depth, guide, 15, 70.0, 50.0, 20.0)
+    err_b = np.abs(b.astype(np.float64) - o64)
+    diff = a != b
+    print(f"\nrefined pixels that changed: {int(diff.sum())}; max regular error with / without refinement: "
+          f"{np.where(act, 0, err_a).max():.2e} / {np.where(act, 0, err_b).max():.2e} mm")
+    assert 0 < diff.sum() < 0.02 * a.size
+    assert np.where(act, 0, err_a).max() <= TOL_MM
+    assert err_a[diff].max() <= err_b[diff].max() + 1e-9
 
 
 @pytest.mark.parametrize("ss,sc,sd,radius", [(70.0, 20.0, 20.0, 3),   # colour guard can fire (sigma_c < 30.6)
@@ -353,10 +380,8 @@ def test_full_size_properties(w, h, radius):
     inner = slice(radius, radius + 16)
     err = np.abs(got[inner].astype(np.float64) - o64[inner])
     act = rule_active_mask(dnp, m64, 2 * radius + 1, 20.0)[inner]
-    tol = TOL_MM + band[inner] + TOL_ACTIVE_MM * act
-    viol = err > tol
-    assert viol.sum() <= 2 and not (viol & ~act).any()
-    assert (err <= TOL_MM).mean() >= 0.98
+    assert np.where(act, 0, err).max() <= TOL_MM
+    assert (act & (err > TOL_MM + band[inner] + TOL_ACTIVE_MM)).sum() <= 2
 
 
 def test_upsample_matches_oracle_definition():
