@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip parity / single-frame / configs[2..4] / strong-scaling blocks")
+    ap.add_argument("--band-size", type=int, default=16384, help="configs[4] frame edge")
     ap.add_argument("--config1", action="store_true",
                     help="configs[0] instead of the headline line: the bundled 640x480 frame, reference defaults "
                          "(window 5, 70/50/20), timed on the host cores and on the GPU, with parity figures")
@@ -117,8 +119,8 @@ def fp32_peak():
 
 
 def measured_traffic(pixels_per_launch: int):
-    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture
-    (dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_jbf_fast_r7_*.ncu.txt), scaled to this
+    """DRAM bytes per launch of the dominant kernel, from the newest committed `ncu --set full` capture
+    (dram__bytes_read.sum + dram__bytes_write.sum of profiles/r*_jbf_fast_r7_*.ncu.txt), scaled to this
     launch's pixel count (traffic is proportional to pixels: every CTA stages one 64x16 tile + halo)."""
     import glob
     import re
@@ -260,6 +262,94 @@ def run_config1(args):
 
 
 # ------------------------------------------------------------------ this framework
+def parity_report(jbf_cls, depth_dev, bgr_dev, frames):
+    """`parity` block: the GPU path against the fp64 evaluation of the reference formula
+    on frames of the configs[1] stream and on configs[0] (bundled colour frame + surrogate depth, reference
+    defaults).  The oracle is the checker here, never the thing measured."""
+    import cv2
+    import numpy as np
+    import torch
+    import oracle
+    from kinectdepthmapenhancement_b200 import synth
+    oracle.build()
+    f = jbf_cls(W, H, *SIGMAS, window_radius=RADIUS)
+    rows = []
+    for i in frames:
+        f.Process(depth_dev[i], bgr_dev[i])
+        out = f.getFiltered_Device().cpu().numpy()
+        guide = f.getSmoothImage_Device().cpu().numpy()
+        pre_ok = bool(np.array_equal(guide, oracle.presmooth(bgr_dev[i].cpu().numpy())))
+        row = oracle.parity_block(out, depth_dev[i].cpu().numpy(), guide, 2 * RADIUS + 1, *SIGMAS)
+        row.update({"frame": int(i), "presmooth_bit_exact": pre_ok})
+        rows.append(row)
+    refined, dropped = f.refine_stats()
+    f.close()
+    img = cv2.imread(os.path.join(ROOT, "tests", "golden", "guide_frame_640x480.png"), 1)
+    d1 = synth.rgbd_frame(W, H, seed=2013, frame=0)[0]
+    f1 = jbf_cls(W, H)
+    f1.Process(d1.cuda(), torch.from_numpy(img).cuda())
+    out1 = f1.getFiltered_Device().cpu().numpy()
+    g1 = f1.getSmoothImage_Device().cpu().numpy()
+    c1 = oracle.parity_block(out1, d1.numpy(), g1, 5, 70.0, 50.0, 20.0)
+    c1["presmooth_bit_exact"] = bool(np.array_equal(g1, oracle.presmooth(img)))
+    c1["workload"] = "configs[0]: bundled colour frame + seeded surrogate depth (depth.xml is a stripped blob), window 5"
+    f1.close()
+    agg = {
+        "tolerance": "mask and indexing bit-exact; |gpu - fp64 oracle| <= 1e-3 mm on every pixel where the reference's "
+                     "skip-if-zero guard is inactive (flat, no conditioning term); guard-active pixels listed",
+        "frames_checked": len(rows), "pixels": sum(r["pixels"] for r in rows),
+        "mask_mismatches": sum(r["mask_mismatches"] for r in rows) + c1["mask_mismatches"],
+        "max_abs_regular_mm": max([r["max_abs_regular_mm"] for r in rows] + [c1["max_abs_regular_mm"]]),
+        "max_abs_active_mm": max([r["max_abs_active_mm"] for r in rows] + [c1["max_abs_active_mm"]]),
+        "n_active": sum(r["n_active"] for r in rows), "n_active_beyond_1e-3": sum(r["n_active_beyond_1e-3"] for r in rows),
+        "frac_within_1e-3": sum(r["frac_within_1e-3"] * r["pixels"] for r in rows) / sum(r["pixels"] for r in rows),
+        "presmooth_bit_exact": all(r["presmooth_bit_exact"] for r in rows) and c1["presmooth_bit_exact"],
+        "refined_fp64_pixels": refined, "refine_queue_dropped": dropped,
+        "stream_frames": rows, "config1": c1,
+    }
+    return agg
+
+
+def e2e_leg(jbf, depth, bgr, out, ne, steps, world, dev, dist, u16: bool):
+    """End to end through jbf_process_host* with library-owned pinned HOST buffers: H2D + Process + D2H in the
+    timed region, host wall clock, max over ranks."""
+    import torch
+    from kinectdepthmapenhancement_b200.jbf import host_buffer
+    ddt = torch.int16 if u16 else torch.float32
+    dh = host_buffer((ne, H, W), ddt)
+    ch = host_buffer((ne, H, W, 3), torch.uint8)
+    oh = host_buffer((ne, H, W), torch.float32)
+    if u16:   # the sensor's format: integer millimetres (xn::DepthMetaData, main.cpp:91-95); bit pattern of uint16
+        dh.copy_(depth[:ne].round().clamp_(0, 65535).to(torch.int32).cpu().to(torch.int16))
+    else:
+        dh.copy_(depth[:ne].cpu())
+    ch.copy_(bgr[:ne].cpu())
+    jbf.process_host(dh, ch, oh)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e_steps = max(2, steps)
+    for _ in range(e_steps):
+        jbf.process_host(dh, ch, oh)   # synchronous: returns when oh is complete
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    res = {"value": world * ne * W * H * e_steps / float(te.item()) / 1e6, "unit": "Mpixel/s",
+           "h2d_bytes_per_step": ne * W * H * (5 if u16 else 7), "d2h_bytes_per_step": ne * W * H * 4,
+           "frames_per_step": ne, "steps": e_steps,
+           "host_gbs_total": world * ne * W * H * (9 if u16 else 11) * e_steps / float(te.item()) / 1e9,
+           "how": ("jbf_process_host_u16: pinned host depth (uint16 mm, the sensor's format) + BGR" if u16 else
+                   "jbf_process_host: pinned host depth (f32) + BGR") +
+                  " -> H2D -> pre-smooth + filter -> D2H, three-slot chunked pipeline on three streams, "
+                  "library-owned cudaHostAlloc buffers; host wall clock, max over ranks"}
+    if not u16 and not torch.equal(oh[:4], out[:4].cpu()):
+        res["warning"] = "e2e output differs from device path"
+    return res
+
+
 def main():
     args = parse()
     if args.config1:
@@ -271,6 +361,7 @@ def main():
     import torch
     import torch.distributed as dist
     from kinectdepthmapenhancement_b200 import JointBilateralFilter, synth
+    from tools import workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -289,7 +380,8 @@ def main():
     depth, bgr = synth.rgbd_stream(n_frames, W, H, seed=1234, first_frame=first, device=dev, distinct=64)
     out = torch.empty_like(depth)
     jbf = JointBilateralFilter(W, H, *SIGMAS, window_radius=RADIUS, max_batch=args.chunk, device=local)
-    launches_per_step = 2 * ((n_frames + args.chunk - 1) // args.chunk)
+    n_chunks = (n_frames + args.chunk - 1) // args.chunk
+    launches_per_step = 3 * n_chunks   # pre-smooth + two-pass filter + fp64 refinement per chunk
 
     def barrier():
         if world > 1:
@@ -298,6 +390,7 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         jbf.process_batch(depth, bgr, out)
+    jbf.refine_stats()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -310,7 +403,9 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # dominant kernel alone: the two-pass filter on the already smoothed guide, same data, same stream
+    refined_per_step = jbf.refine_stats()[0] / max(1, args.steps)
+    # dominant kernel alone: the two-pass filter (+ its fp64 refinement launch) on the already smoothed guide,
+    # same data, same stream
     guide4 = jbf.presmooth(bgr[:args.chunk])
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -333,30 +428,33 @@ def main():
     value = total_pixels / (ms_max * 1e-3) / 1e6
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    e2e = None
+    e2e = e2e_u16 = None
     if not args.no_e2e:
         ne = min(args.e2e_frames, n_frames)
-        dh = depth[:ne].cpu().pin_memory()
-        ch = bgr[:ne].cpu().pin_memory()
-        oh = torch.empty_like(dh).pin_memory()
-        jbf.process_host(dh, ch, oh)
-        barrier()
-        t0 = time.perf_counter()
-        e_steps = max(2, args.steps)
-        for _ in range(e_steps):
-            jbf.process_host(dh, ch, oh)   # synchronous: returns when oh is complete
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * ne * W * H * e_steps / float(te.item()) / 1e6, "unit": "Mpixel/s",
-               "h2d_bytes_per_step": ne * W * H * 7, "d2h_bytes_per_step": ne * W * H * 4,
-               "frames_per_step": ne, "steps": e_steps,
-               "how": "jbf_process_host: pinned host depth+BGR -> H2D -> pre-smooth + filter -> D2H, "
-                      "three-slot chunked pipeline on three streams; host wall clock, max over ranks"}
-        if not torch.equal(oh[: args.chunk], out[: args.chunk].cpu()):
-            e2e["warning"] = "e2e output differs from device path"
+        e2e = e2e_leg(jbf, depth, bgr, out, ne, args.steps, world, dev, dist, u16=False)
+        e2e_u16 = e2e_leg(jbf, depth, bgr, out, ne, args.steps, world, dev, dist, u16=True)
+
+    # ---- secondary workloads (every rank takes part in the collective ones)
+    extra = {}
+    if not args.no_extra:
+        extra["strong"] = workloads.strong(jbf, depth, bgr, out, min(4096, n_frames * world))
+        parity = parity_report(JointBilateralFilter, depth, bgr, (0, 17, 33, 63)) if rank == 0 else None
+        del depth, bgr, out, guide4
+        jbf.close()
+        torch.cuda.empty_cache()
+        for mode in (("nccl",) if world == 1 else ("nccl", "peer")):
+            try:
+                extra["bands_" + mode] = workloads.bands(args.band_size, 9, peer=(mode == "peer"))
+            except Exception as e:   # noqa: BLE001 -- reported, never hidden
+                extra["bands_" + mode] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        if rank == 0:
+            peaks0, _ = measured_peaks()
+            extra["single_frame"] = workloads.single()
+            extra["upsample"] = workloads.upsample()
+            extra["sweep"] = workloads.sweep(hbm_gbs=peaks0["hbm_gbs"])
+    else:
+        parity = None
 
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
@@ -365,6 +463,8 @@ def main():
         ach_tf = px_per_launch * FLOP_PER_PIXEL / (kern_ms * 1e-3) / 1e12
         ach_gbs = px_per_launch * BYTES_PER_PIXEL / (kern_ms * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(px_per_launch)
+        taps_per_s = px_per_launch * (2 * RADIUS + 1) ** 2 / (kern_ms * 1e-3)
+        mufu_peak = (micro or {}).get("mufu_ex2_ginst_s", 148 * 16 * 1.965) * 1e9
         line = {
             "metric": "JBF Mpixel/s at 640x480 r=7", "value": value, "unit": "Mpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
@@ -373,19 +473,30 @@ def main():
                                    "70/50/20, guide pre-smooth (5,30,30), frame-sharded",
                        "frames_per_gpu": n_frames, "frames_per_launch": args.chunk, "parallelism": f"frames x{world}",
                        "l2": "inputs (8.8 GB/GPU) larger than L2; no flush needed"},
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "e2e": e2e, "e2e_u16": e2e_u16, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "refined_fp64_pixels_per_step": refined_per_step,
             "roofline": {
-                "kernel": "jbf_fast_kernel<7,64,16> (two-pass filter; presmooth_kernel is the other launch)",
+                "kernel": "jbf_fast_kernel<7,64,16> two-pass filter + jbf_refine_kernel (fp64 re-evaluation of the "
+                          "ill-conditioned pixels); presmooth5_kernel is the other launch",
                 "bound": "fp32", "achieved": ach_tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": ach_tf / fp32_tf,
-                "peak_source": fp32_src, "flop_per_pixel": FLOP_PER_PIXEL, "pixels_per_launch": px_per_launch,
+                "peak_source": fp32_src, "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach_tf / FP32_NOMINAL_TFLOPS,
+                "flop_per_pixel": FLOP_PER_PIXEL,
+                "flop_note": "ALGORITHMIC flops of the reference kernel text (33 flop + 3 exp per tap, SURVEY.md 8(d)); the "
+                             "kernel executes ~15 fp32 flop + 2 MUFU.EX2 + 2 integer SIMD ops per tap, so this is not "
+                             "hardware FP32 utilisation -- the issue-level bound is `mufu` below",
+                "mufu": {"achieved_gtaps_s": taps_per_s / 1e9, "ex2_per_tap": 2,
+                         "peak_gex2_s": mufu_peak / 1e9, "frac": 2 * taps_per_s / mufu_peak,
+                         "peak_source": "MUFU.EX2 issue rate measured this run (tools/pipe_microbench)" if micro else "nominal 16/clk/SM"},
+                "pixels_per_launch": px_per_launch,
                 "kernel_ms_per_launch": kern_ms, "kernel_mpixel_s": px_per_launch / (kern_ms * 1e-3) / 1e6,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                         "peak_source": peaks_kind + " (MEASURED_PEAKS.json)", "bytes_per_pixel": BYTES_PER_PIXEL},
-                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic": traffic, "traffic_source": ("static: " + traffic_src + " (one ncu --set full capture of this kernel, "
+                                                       "scaled by pixels; not measured in this run)") if traffic_src else None,
                 "algorithmic_bytes_per_launch": px_per_launch * BYTES_PER_PIXEL,
                 "note": "the path is FP32/MUFU-issue bound (intensity 675 flop/B vs balance ~11), see DESIGN.md",
             },
-            "microbench": micro,
+            "parity": parity, "extra": extra, "microbench": micro,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)

@@ -127,6 +127,18 @@ int jbf_filter_rows_p2p(jbf_handle *h, const float *depth_dev, const uint8_t *gu
 int jbf_process_host(jbf_handle *h, const float *depth_host, const uint8_t *bgr_host, size_t bgr_step,
                      float *out_host, int n_frames);
 
+/* Same pipeline with the depth in the sensor's own format: uint16 millimetres, as xn::DepthMetaData holds it
+ * (main.cpp:91-95; Buffer2D::insertData(xn::DepthMetaData*) converts it to float on the host before the
+ * upload, Buffer2D.cpp:18-32).  Here the 2-byte samples are uploaded and converted on the device:
+ * 5 instead of 7 bytes per pixel cross PCIe. */
+int jbf_process_host_u16(jbf_handle *h, const uint16_t *depth_host, const uint8_t *bgr_host, size_t bgr_step,
+                         float *out_host, int n_frames);
+
+/* Page-locked host memory for those buffers (cudaHostAlloc, portable).  write_combined != 0: for buffers the
+ * CPU only writes front to back (sensor frames); never for the result buffer.  NULL on failure. */
+void *kdme_host_alloc(size_t bytes, int write_combined);
+void kdme_host_free(void *p);
+
 /* float* JointBilateralFilter::getFiltered_Device() const -- JointBilateralFilter.cpp:41-43.
  * Borrowed pointer, valid until the next jbf_process / jbf_destroy. */
 float *jbf_filtered_device(jbf_handle *h);

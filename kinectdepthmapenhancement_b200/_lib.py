@@ -51,6 +51,9 @@ SIGNATURES = {
     "jbf_filter_guide4": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
     "jbf_presmooth": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
     "jbf_process_host": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
+    "jbf_process_host_u16": (_i, [_vp, _vp, _vp, _sz, _vp, _i]),
+    "kdme_host_alloc": (_vp, [_sz, _i]),
+    "kdme_host_free": (None, [_vp]),
     "jbf_presmooth_rows": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
     "jbf_filter_rows": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i, _i]),
     "jbf_presmooth_rows_p2p": (_i, [_vp, _vp, _sz, _vp, _sz, _i, _i, _i, _vp, _vp]),

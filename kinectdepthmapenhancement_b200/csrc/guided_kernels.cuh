@@ -174,6 +174,157 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_kernel(const __grid_const
     p.out[(long long)gy * p.width + gx] = o;
 }
 
+// -----------------------------------------------------------------------------
+// Fast form of the same three sweeps for the common case: compile-time radius (fully unrolled window, no
+// index arithmetic), branch-free taps (validity / label tests become selects), the log2-domain spatial LUT
+// read straight from the constant bank as an FFMA operand, the colour distance through the 2^23 magic
+// accumulator (no int->float conversion), one MUFU.RCP instead of an IEEE division per sweep-3 tap, and
+// the same-label predicate of sweep 1 kept as a bit mask for sweep 2.  Preconditions (host-checked): the
+// colour skip-if-zero guard cannot fire in sweep 1 (sigma_c >= 30.63) and sigma_c, sigma_d != 0.  The
+// per-valid-tap colour-sigma recurrence, its underflow to 0 and the -0/0 NaN poisoning are kept exactly.
+template <int R>
+struct GuidedFastParams {
+    int width, height;
+    const float* depth;
+    const int32_t* labels;  // nullable
+    const uint8_t* bgr;
+    long long bgr_step;
+    float* out;
+    float sigma_c, nk0 /* -log2e/(2 sigma_c^2) */, sq /* sqrt(log2e/(2 sigma_d^2)) */;
+    const float* depth_lo;
+    int wl, hl;
+    float ltab[(2 * R + 1) * (2 * R + 1)];   // log2(S_ij) + kWeightBias, or kWeightBias where S_ij == 0
+};
+
+template <int R, int TW, int TH>
+__global__ void __launch_bounds__(TW * TH) guided_fill_fast_kernel(const __grid_constant__ GuidedFastParams<R> p) {
+    constexpr int NT = TW * TH, WS = 2 * R + 1, SP = TW + 2 * R, SH = TH + 2 * R;
+    static_assert(WS * WS <= 64, "the same-label mask is one 64-bit word");
+    __shared__ float sD[SP * SH];
+    __shared__ uint32_t sG[SP * SH];
+    __shared__ int32_t sLab[SP * SH];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int idx = tid; idx < SP * SH; idx += NT) {
+        int sy = idx / SP, sx = idx - sy * SP;
+        int gx = x0 - R + sx, gy = y0 - R + sy;
+        bool in = (gx >= 0) & (gx < p.width) & (gy >= 0) & (gy < p.height);
+        float d = 0.f;
+        uint32_t g = 0u;
+        int32_t l = 0;
+        if (in) {
+            const long long k = (long long)gy * p.width + gx;
+            if (p.depth_lo) {
+                const int xl = guided_upsample_site(gx, p.width, p.wl), yl = guided_upsample_site(gy, p.height, p.hl);
+                if ((xl >= 0) & (yl >= 0)) d = __ldg(p.depth_lo + (long long)yl * p.wl + xl);
+            } else {
+                d = __ldg(p.depth + k);
+            }
+            const uint8_t* q = p.bgr + (long long)gy * p.bgr_step + 3 * gx;
+            g = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+            if (p.labels) l = __ldg(p.labels + k);
+        }
+        sD[idx] = (d > kValidDepth) ? d : 0.f;
+        sG[idx] = g;
+        sLab[idx] = l;
+    }
+    __syncthreads();
+    const int lx = tid % TW, ly = tid / TW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= p.width || gy >= p.height) return;
+    const int base = ly * SP + lx;
+    const uint32_t gpix = sG[base + R * SP + R];
+    const int32_t lp = sLab[base + R * SP + R];
+    // accumulation origin: the centre sample, else the first sample of the window (rare, divergent)
+    float d0 = sD[base + R * SP + R];
+    if (d0 == 0.f) {
+        for (int t = 0; t < WS * WS && d0 == 0.f; ++t) d0 = sD[base + (t / WS) * SP + (t % WS)];
+    }
+    const float nk0 = p.nk0;
+
+    // ---- sweep 1: same-label weighted mean (:116-139)
+    float acc = 0.f, wsum = 0.f;
+    unsigned long long same = 0ull;
+#pragma unroll
+    for (int i = 0; i < WS; ++i)
+#pragma unroll
+        for (int j = 0; j < WS; ++j) {
+            const int q = base + i * SP + j;
+            const float d = sD[q];
+            const bool pr = (d != 0.f) & (sLab[q] == lp);
+            const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+            const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;
+            float f = ex2_approx(fmaf(cdf, nk0, p.ltab[i * WS + j]));
+            f = pr ? f : 0.f;
+            acc = fmaf(f, d - d0, acc);
+            wsum += f;
+            same |= pr ? (1ull << (i * WS + j)) : 0ull;
+        }
+    float o = 0.f;
+    if (wsum > 0.f) {
+        const float delta = acc / wsum;   // mean = d0 + delta
+        const float mean = d0 + delta;    // the reference's fp32 w_average
+        // ---- sweep 2: mean absolute deviation of the same taps (:143-156)
+        float dev = 0.f;
+#pragma unroll
+        for (int i = 0; i < WS; ++i)
+#pragma unroll
+            for (int j = 0; j < WS; ++j) {
+                const float x = fabsf((sD[base + i * SP + j] - d0) - delta);
+                dev += ((same >> (i * WS + j)) & 1ull) ? x : 0.f;
+            }
+        const int count = __popcll(same);
+        if (count != 0) dev /= (float)count;
+        // 5.0*deviation/pow(w_average,2.0f): double expression, fp32 square (:171)
+        const float adaptive = (float)(5.0 * (double)dev / (double)(mean * mean));
+        // ---- sweep 3: all samples, mutating colour sigma (:158-195)
+        const float kZero = -(float)kExpZeroArg;
+        const float l2e = (float)kLog2e;
+        const float sq = p.sq;
+        const float e_thr = (float)1.2247448713915890e1;  // sqrt(150)
+        float sigma = p.sigma_c;
+        float num = 0.f, den = 0.f;
+        bool poisoned = false;
+#pragma unroll
+        for (int i = 0; i < WS; ++i)
+#pragma unroll
+            for (int j = 0; j < WS; ++j) {
+                const int q = base + i * SP + j;
+                const float d = sD[q];
+                const bool v = d != 0.f;
+                const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+                const float cd = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;
+                float lg = p.ltab[i * WS + j];
+                // the recurrence advances once per VALID tap while sigma != 0 (:170-176)
+                const bool adv = v & (sigma != 0.0f);
+                const float t = sigma * 0.3f;
+                const float sn = (adaptive > t) ? adaptive : t;
+                sigma = adv ? sn : sigma;
+                const float dn = 2 * (sigma * sigma);
+                if (dn > 1.0e-30f) {
+                    float rc;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dn));
+                    const float a = -cd * rc;
+                    if (adv & (a >= kZero)) lg = fmaf(a, l2e, lg);
+                } else if (adv & (cd == 0.f)) {
+                    // cd >= 1 over a denominator <= 1e-30 is beyond the fp32 expf() cut-off: factor skipped.
+                    // cd == 0: -0/dn = -0 (factor 1) unless sigma^2 underflowed to 0: -0/0 = NaN poisons the pixel
+                    if (dn == 0.f) poisoned = true;
+                }
+                const float e = (d - d0) - delta;
+                const float es = e * sq;
+                if (!(fabsf(es) > e_thr)) lg = fmaf(-es, es, lg);
+                float f = ex2_approx(lg);
+                f = v ? f : 0.f;
+                num = fmaf(f, e, num);
+                den += f;
+            }
+        if (poisoned) o = __int_as_float(0x7fc00000);
+        else o = (den == 0.0f) ? 0.0f : mean + num / den;
+    }
+    p.out[(long long)gy * p.width + gx] = o;
+}
+
 // MarkovRandomField.cu:4-40: out = (d_p + sum f d_q) / (1 + sum f), f = smooth * expf(-sigma_c * cd)
 // over valid taps; evaluated as d_p + sum f (d_q - d_p) / (1 + sum f).
 template <int TW, int TH>

@@ -61,6 +61,10 @@ struct JbfParams {
     // tiles start vertically, so a band equals the same rows of the whole image bit for bit.
     // Whole-image mode: y_off = 0, out_rows = height.
     int y_off, out_rows;
+    // load balance of small launches: tile rows [0, nbig_rows) have the template's height TH, the rows below
+    // are cut into tiles of `ts` rows (a multiple of 2: whole warps), so that the work beyond a whole number
+    // of big tiles per SM is spread over many SMs instead of landing on a few.  All big: nbig_rows = INT_MAX.
+    int nbig_rows, ts;
     // peer-memory halos (row bands over NVLink): rows [band0, band1) of the arrays are this rank's own;
     // when depth_up / depth_dn are non-null, rows above / below are read straight from the neighbour
     // GPU's band through these peer-mapped pointers (depth_up + row*W for row < band0,
@@ -134,7 +138,11 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_fast + 3 * T::PLANE + 2 * T::LBYTES);
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = p.y_off + blockIdx.y * TH, frame = blockIdx.z;
+    const bool big = (int)blockIdx.y < p.nbig_rows;
+    const int th_eff = big ? TH : p.ts;                       // rows of this tile
+    const int she = th_eff + 2 * R;                           // staged rows this tile needs
+    const int x0 = blockIdx.x * TW, frame = blockIdx.z;
+    const int y0 = p.y_off + (big ? (int)blockIdx.y * TH : p.nbig_rows * TH + ((int)blockIdx.y - p.nbig_rows) * p.ts);
     const int sx0 = x0 - RP, sy0 = y0 - R;  // image coords of staged (0,0)
     // a tile whose halo crosses into a neighbour GPU's rows stages with plain loads (peer pointers);
     // every other tile keeps the launch's staging mode (CTA-uniform)
@@ -187,7 +195,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             }
             __syncthreads();
         }
-        for (int idx = tid; idx < SP * SH; idx += NT) {
+        for (int idx = tid; idx < SP * she; idx += NT) {
             int sy = idx / SP, sx = idx - sy * SP;
             int gx = sx0 + sx, gy = sy0 + sy;
             bool in = (gx >= 0) & (gx < p.width) & (gy >= 0) & (gy < p.height);
@@ -213,7 +221,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     __syncthreads();
 
     // ---------------- stage B: validity word per staged sample; holes (and NaN) read as depth 0
-    for (int idx = tid; idx < SP * SH; idx += NT) {
+    for (int idx = tid; idx < SP * she; idx += NT) {
         const float d = sD[idx];
         const bool v = d > kValidDepth;
         sD[idx] = v ? d : 0.f;
@@ -223,6 +231,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
 
     // ---------------- compute: 4 pixels per thread
     const int lx = tid % (TW / 4), ly = tid / (TW / 4);
+    if (ly >= th_eff) return;   // short tile: whole warps leave (th_eff is even, a tile row is 16 threads)
     const int colbase = 4 * lx;  // staged column of the fetched segment's first word
     uint32_t gp[4];
     float d0 = 0.f;
@@ -494,6 +503,239 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 for (int k = 0; k < 4; ++k)
                     if (gx + k < p.width) { xdst[3 * k] = v3[3 * k]; xdst[3 * k + 1] = v3[3 * k + 1]; xdst[3 * k + 2] = v3[3 * k + 2]; }
             }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------
+// Upsampling in gather form (declared only in the reference,
+// JointBilateralFilter.h:14).  The sparse high-res depth image is never materialised: a low-res sample
+// (xl, yl) lives at high-res site (floor((2 xl + 1) W / (2 wl)), floor((2 yl + 1) H / (2 hl))), and a
+// pixel's window only meets the ~(2r+1)^2 wl hl / (W H) sites of that lattice.  One CTA stages the sites
+// its tile can see (low-res depth + the smoothed guide AT the site); each thread owns 4 adjacent pixels and
+// sweeps site rows x site columns.  The arithmetic per pixel is the dense kernel's, tap for tap and in the
+// same order (taps that are not sites have weight exactly 0 there and add nothing), so the result equals
+// jbf_fast_kernel on the materialised sparse image BIT FOR BIT -- including the accumulation origin rule,
+// the 2Sum row partials and the fp64 refinement queue.
+struct UpsampleGeom {
+    int ncol_max, nrow_max;      // staged site columns / rows per tile (host-computed bound)
+    int radius;
+    const float* ltab1;          // [(2r+1)][(2r+1)] log2(S)+bias1   (pass 1)
+    const float* ltab2;          // [(2r+1)][(2r+1)] log2(S)+kWeightBias (pass 2)
+};
+
+// first low-res index whose site is >= x
+__device__ __forceinline__ int upsample_first_site_at_or_after(int x, int W, int wl) {
+    if (x <= 0) return 0;
+    long long num = 2LL * wl * x - W;                       // site(xl) >= x  <=>  (2xl+1) W >= 2 wl x  (floor is monotone)
+    int xl = (num <= 0) ? 0 : (int)((num + 2LL * W - 1) / (2LL * W));
+    while (xl > 0 && (int)(((2LL * (xl - 1) + 1) * W) / (2LL * wl)) >= x) --xl;
+    while (xl < wl && (int)(((2LL * xl + 1) * W) / (2LL * wl)) < x) ++xl;
+    return xl;
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__((TW / 4) * TH)
+jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
+    constexpr int NT = (TW / 4) * TH;
+    const int R = g.radius, WS = 2 * R + 1;
+    extern __shared__ __align__(16) uint8_t smem_up[];
+    float* sSd = reinterpret_cast<float*>(smem_up);                      // [nrow_max][ncol_max] sample depth (0 = hole)
+    uint32_t* sSg = reinterpret_cast<uint32_t*>(sSd + g.nrow_max * g.ncol_max);   // guide word at the site
+    int* sXs = reinterpret_cast<int*>(sSg + g.nrow_max * g.ncol_max);    // [ncol_max] site x
+    int* sYs = sXs + g.ncol_max;                                         // [nrow_max] site y
+    float* sL1 = reinterpret_cast<float*>(sYs + g.nrow_max);             // [WS][WS]
+    float* sL2 = sL1 + WS * WS;
+    __shared__ int sN[2];
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int idx = tid; idx < WS * WS; idx += NT) { sL1[idx] = __ldg(g.ltab1 + idx); sL2[idx] = __ldg(g.ltab2 + idx); }
+    grid_dependency_wait();
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.q_count_prev = 0u;
+    // site columns with x in [x0 - R, x0 + TW - 1 + R], site rows with y in [y0 - R, y0 + TH - 1 + R]
+    const int xl0 = upsample_first_site_at_or_after(x0 - R, p.width, p.wl);
+    const int yl0 = upsample_first_site_at_or_after(y0 - R, p.height, p.hl);
+    for (int t = tid; t < g.ncol_max + g.nrow_max; t += NT) {
+        if (t < g.ncol_max) {
+            const int xl = xl0 + t;
+            const int xs = (xl < p.wl) ? (int)(((2LL * xl + 1) * p.width) / (2LL * p.wl)) : 0x3fffffff;
+            sXs[t] = (xs <= x0 + TW - 1 + R) ? xs : 0x3fffffff;
+        } else {
+            const int yl = yl0 + (t - g.ncol_max);
+            const int ys = (yl < p.hl) ? (int)(((2LL * yl + 1) * p.height) / (2LL * p.hl)) : 0x3fffffff;
+            sYs[t - g.ncol_max] = (ys <= y0 + TH - 1 + R) ? ys : 0x3fffffff;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nc = 0, nr = 0;
+        while (nc < g.ncol_max && sXs[nc] != 0x3fffffff) ++nc;
+        while (nr < g.nrow_max && sYs[nr] != 0x3fffffff) ++nr;
+        sN[0] = nc; sN[1] = nr;
+    }
+    __syncthreads();
+    const int ncol = sN[0], nrow = sN[1];
+    for (int idx = tid; idx < ncol * nrow; idx += NT) {
+        const int sr = idx / ncol, sc = idx - sr * ncol;
+        const float d = __ldg(p.depth_lo + (long long)(yl0 + sr) * p.wl + (xl0 + sc));
+        sSd[sr * g.ncol_max + sc] = (d > kValidDepth) ? d : 0.f;
+        sSg[sr * g.ncol_max + sc] = __ldg(p.guide4 + (long long)sYs[sr] * p.guide_pitch + sXs[sc]);
+    }
+    __syncthreads();
+
+    const int lx = tid % (TW / 4), ly = tid / (TW / 4);
+    const int gy = y0 + ly, gx = x0 + 4 * lx;
+    uint32_t gp[4] = {0u, 0u, 0u, 0u};
+    if (gy < p.height) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (gx + k < p.width) gp[k] = __ldg(p.guide4 + (long long)gy * p.guide_pitch + gx + k);
+    }
+    // this thread's site rows [r_lo, r_hi) and site columns [c_lo, c_hi) (union over its 4 pixels)
+    int r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
+    while (r_lo < nrow && sYs[r_lo] < gy - R) ++r_lo;
+    r_hi = r_lo;
+    while (r_hi < nrow && sYs[r_hi] <= gy + R) ++r_hi;
+    while (c_lo < ncol && sXs[c_lo] < gx - R) ++c_lo;
+    c_hi = c_lo;
+    while (c_hi < ncol && sXs[c_hi] <= gx + 3 + R) ++c_hi;
+
+    // accumulation origin, the dense kernel's rule: first valid own pixel, else the first valid sample of the
+    // thread's windows -- own row first, then top to bottom, columns ascending
+    float d0 = 0.f;
+    {
+        bool has = false;
+        int own = -1;
+        for (int sr = r_lo; sr < r_hi; ++sr) if (sYs[sr] == gy) own = sr;
+        if (own >= 0)
+            for (int sc = c_lo; sc < c_hi && !has; ++sc)
+                if (sXs[sc] >= gx && sXs[sc] <= gx + 3 && sSd[own * g.ncol_max + sc] != 0.f) { d0 = sSd[own * g.ncol_max + sc]; has = true; }
+        if (!has && own >= 0)
+            for (int sc = c_lo; sc < c_hi && !has; ++sc)
+                if (sSd[own * g.ncol_max + sc] != 0.f) { d0 = sSd[own * g.ncol_max + sc]; has = true; }
+        for (int sr = r_lo; sr < r_hi && !has; ++sr)
+            for (int sc = c_lo; sc < c_hi && !has; ++sc)
+                if (sSd[sr * g.ncol_max + sc] != 0.f) { d0 = sSd[sr * g.ncol_max + sc]; has = true; }
+    }
+    const float sq = p.sq;
+    const float cO = __fmul_rn(d0, sq);
+    const float c_err = fmaf(d0, sq, -cO);
+    const float ncO = -cO;
+    const float nkc = p.nkc;
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f}, accl[4] = {0.f, 0.f, 0.f, 0.f}, wsl[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sr = r_lo; sr < r_hi; ++sr) {
+        const int i = sYs[sr] - gy + R;
+        float racc[4] = {0.f, 0.f, 0.f, 0.f}, rws[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sc = c_lo; sc < c_hi; ++sc) {
+            const float d = sSd[sr * g.ncol_max + sc];
+            if (d == 0.f) continue;
+            const uint32_t gq = sSg[sr * g.ncol_max + sc];
+            const float dsh = fmaf(d, sq, ncO);
+            const int jb = sXs[sc] - gx + R;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = jb - k;
+                if (j >= 0 && j < WS) {
+                    const uint32_t ad = __vabsdiffu4(gp[k], gq);
+                    const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;   // exact integer, no I2F
+                    const float f = ex2_approx(fmaf(cdf, nkc, sL1[i * WS + j]));
+                    racc[k] = fmaf(f, dsh, racc[k]);
+                    rws[k] += f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // Knuth 2Sum, as two_sum2 does per lane
+            float s_ = acc[k] + racc[k], bb = s_ - acc[k];
+            accl[k] += (acc[k] - (s_ - bb)) + (racc[k] - bb);
+            acc[k] = s_;
+            s_ = wsum[k] + rws[k]; bb = s_ - wsum[k];
+            wsl[k] += (wsum[k] - (s_ - bb)) + (rws[k] - bb);
+            wsum[k] = s_;
+        }
+    }
+    float delta[4];
+    bool any[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        any[k] = wsum[k] > 0.f;
+        const float dh = acc[k] / wsum[k];
+        float res = fmaf(-dh, wsum[k], acc[k]);
+        res += accl[k];
+        res = fmaf(-dh, wsl[k], res);
+        delta[k] = any[k] ? (dh + res / wsum[k]) : 0.f;
+    }
+    const float e_thr = p.e_thr;
+    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sr = r_lo; sr < r_hi; ++sr) {
+        const int i = sYs[sr] - gy + R;
+        float rnum[4] = {0.f, 0.f, 0.f, 0.f}, rden[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sc = c_lo; sc < c_hi; ++sc) {
+            const float d = sSd[sr * g.ncol_max + sc];
+            if (d == 0.f) continue;
+            const uint32_t gq = sSg[sr * g.ncol_max + sc];
+            const float dsh = fmaf(d, sq, ncO);
+            const int jb = sXs[sc] - gx + R;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = jb - k;
+                if (j >= 0 && j < WS) {
+                    const uint32_t ad = __vabsdiffu4(gp[k], gq);
+                    const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;   // exact integer, no I2F
+                    float arg = fmaf(cdf, nkc, sL2[i * WS + j]);
+                    const float e = dsh - delta[k];
+                    if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
+                    const float f = ex2_approx(arg);
+                    rnum[k] = fmaf(f, e, rnum[k]);
+                    rden[k] += f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { num[k] += rnum[k]; den[k] += rden[k]; }
+    }
+
+    float o[4];
+    bool flag[4];
+    bool anyflag = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float t = (delta[k] + num[k] / den[k]) - c_err;
+        o[k] = any[k] ? fmaf(t, p.inv_sq, d0) : 0.f;
+        flag[k] = any[k] && !(den[k] >= wsum[k] * p.flag_scale);
+        anyflag |= flag[k];
+    }
+    if (__any_sync(0xffffffffu, anyflag)) {
+        const int lane = tid & 31;
+        unsigned m[4];
+        int total = 0, before = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            m[k] = __ballot_sync(0xffffffffu, flag[k] && gy < p.height && gx + k < p.width);
+            before += __popc(m[k] & ((1u << lane) - 1u));
+            total += __popc(m[k]);
+        }
+        unsigned base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(p.q_count, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((m[k] >> lane) & 1u) {
+                const unsigned slot = base + (unsigned)before;
+                ++before;
+                if (slot < p.q_capacity) p.q_items[slot] = (unsigned)((long long)gy * p.width + gx + k);
+            }
+    }
+    if (gy < p.height && gx < p.width) {
+        float* dst = p.out + (long long)gy * p.width + gx;
+        if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            stg_stream_f4(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (gx + k < p.width) dst[k] = o[k];
         }
     }
 }

@@ -110,12 +110,13 @@ struct jbf_handle {
     size_t q_capacity = 0;
     float bias1 = 0.f, flag_scale = 0.f;
     double kc = 0, kd = 0;
-    float* ltab_generic_dev = nullptr;  // [WS][WS]
+    float* ltab_generic_dev = nullptr;  // [WS][WS], bias kWeightBias
+    float* ltab_generic1_dev = nullptr; // [WS][WS], bias bias1 (pass 1 of the gather-form upsampling)
     // derived
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
-    bool force_no_tma = false, force_big_tiles = false, no_refine = false;
+    bool force_no_tma = false, force_big_tiles = false, no_refine = false, no_split_tiles = false;
     int force_tile_h = 0;
     int last_variant = 0;
     // TMA descriptors of the last fast launch, reused while (pointers, rows, frames, box) are unchanged
@@ -127,6 +128,7 @@ struct jbf_handle {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[kPipeDepth] = {}, ev_done[kPipeDepth] = {}, ev_free[kPipeDepth] = {};
     float* pipe_depth[kPipeDepth] = {};
+    uint16_t* pipe_depth16[kPipeDepth] = {};   // u16 sensor depth staging (jbf_process_host_u16), lazy
     uint8_t* pipe_bgr[kPipeDepth] = {};
     float* pipe_out[kPipeDepth] = {};
     size_t pipe_bgr_step = 0;
@@ -134,6 +136,7 @@ struct jbf_handle {
 };
 
 static bool fast_radius_available(int r);
+static int buf_blocks(long long n);
 
 // calcSpatialFilter -- JointBilateralFilter.cpp:31-40, fp32 on the host as the reference does.
 static void host_spatial_lut(std::vector<float>& lut, int ws, float sigma_s) {
@@ -190,6 +193,15 @@ static int build_tables(jbf_handle* h) {
     CK(cudaMalloc(&h->ltab_pairs1_dev, lpairs1.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->ltab_pairs1_dev, lpairs1.data(), lpairs1.size() * sizeof(float), cudaMemcpyHostToDevice,
                        h->stream));
+    {
+        std::vector<float> lg1(lg.size());
+        for (size_t i = 0; i < lg.size(); i++) {
+            const float sv = lut[i];
+            lg1[i] = (sv != 0.0f && std::isfinite(sv)) ? (float)(std::log2((double)sv) + (double)h->bias1) : h->bias1;
+        }
+        CK(cudaMalloc(&h->ltab_generic1_dev, lg1.size() * sizeof(float)));
+        CK(cudaMemcpy(h->ltab_generic1_dev, lg1.data(), lg1.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&h->slut_dev, lut.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->slut_dev, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMalloc(&h->stats_dev, 2 * sizeof(unsigned long long)));
@@ -238,6 +250,7 @@ static int build_tables(jbf_handle* h) {
     h->force_no_tma = getenv("KDME_NO_TMA") != nullptr;
     h->force_big_tiles = getenv("KDME_BIG_TILES") != nullptr;
     h->no_refine = getenv("KDME_NO_REFINE") != nullptr;
+    h->no_split_tiles = getenv("KDME_NO_SPLIT_TILES") != nullptr;
     if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
     h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
     h->kd = h->use_depth ? 1.0 / (2.0 * (double)h->sigma_d * (double)h->sigma_d) : 0.0;
@@ -320,10 +333,11 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->q_count_dev);
     cudaFree(h->q_items_dev);
     cudaFree(h->ltab_generic_dev);
+    cudaFree(h->ltab_generic1_dev);
     cudaFree(h->ps_space_dev);
     cudaFree(h->ps_color_dev);
     for (int b = 0; b < kPipeDepth; b++) {
-        cudaFree(h->pipe_depth[b]); cudaFree(h->pipe_bgr[b]); cudaFree(h->pipe_out[b]);
+        cudaFree(h->pipe_depth[b]); cudaFree(h->pipe_bgr[b]); cudaFree(h->pipe_out[b]); cudaFree(h->pipe_depth16[b]);
         if (h->ev_in[b]) cudaEventDestroy(h->ev_in[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
         if (h->ev_free[b]) cudaEventDestroy(h->ev_free[b]);
@@ -414,8 +428,20 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, b
         if (want_tma) p.mode = kStageTma;
     }
     h->last_variant = (p.mode == kStageTma ? 0x100 : 0) | (TH == 8 ? 0x200 : 0) | (TH == 4 ? 0x800 : 0) | 0x400;
+    // Small launches: keep a whole number of TH-row tiles per SM and cut the image rows left over into 2-row
+    // tiles (one warp each), so the surplus spreads over many SMs instead of giving a few SMs one more big tile.
+    const int tx = (p.width + TW - 1) / TW;
+    int tile_rows = (p.out_rows + TH - 1) / TH;
+    p.nbig_rows = INT_MAX; p.ts = 2;
+    const long long ctas = (long long)tx * tile_rows * p.n_frames;
+    if (!h->no_split_tiles && TH > 2 && ctas < 148LL * 12 && ctas % 148 != 0) {
+        const long long per_sm = ctas / 148;
+        const int nbig = (int)std::min<long long>(tile_rows, (per_sm * 148) / ((long long)tx * p.n_frames));
+        const int rem = p.out_rows - nbig * TH;
+        if (nbig >= 1 && rem > 0) { p.nbig_rows = nbig; tile_rows = nbig + (rem + p.ts - 1) / p.ts; }
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((p.width + TW - 1) / TW, (p.out_rows + TH - 1) / TH, p.n_frames);
+    cfg.gridDim = dim3(tx, tile_rows, p.n_frames);
     cfg.blockDim = dim3(T::NT);
     cfg.dynamicSmemBytes = T::SMEM;
     cfg.stream = h->stream;
@@ -501,6 +527,41 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
         }
         p.q_items = h->q_items_dev; p.q_capacity = (unsigned)h->q_capacity;
         int rc = KDME_ENOTSUP;
+        if (p.mode == kStageUpsample && !getenv("KDME_UPSAMPLE_DENSE") && !p.xyz) {
+            // gather form: only the sites of the low-res lattice are visited (bit-identical to the dense form)
+            constexpr int TW = 64, TH = 16;
+            UpsampleGeom g;
+            g.radius = h->radius;
+            g.ncol_max = (int)(((long long)(TW + 2 * h->radius) * wl + h->width - 1) / h->width) + 2;
+            g.nrow_max = (int)(((long long)(TH + 2 * h->radius) * hl + rows - 1) / rows) + 2;
+            g.ltab1 = h->ltab_generic1_dev;
+            g.ltab2 = h->ltab_generic_dev;
+            const int ws_ = 2 * h->radius + 1;
+            const size_t smem = (size_t)g.ncol_max * g.nrow_max * 8 + (size_t)(g.ncol_max + g.nrow_max) * 4 +
+                                (size_t)ws_ * ws_ * 8 + 16;
+            if (smem <= 200 * 1024) {
+                static std::atomic<unsigned long long> attr_done{0};
+                const unsigned long long bit = 1ull << (h->device & 63);
+                if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+                    CK(cudaFuncSetAttribute(jbf_upsample_gather_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    attr_done.fetch_or(bit, std::memory_order_release);
+                }
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((p.width + TW - 1) / TW, (rows + TH - 1) / TH, 1);
+                cfg.blockDim = dim3((TW / 4) * TH);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = h->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = pdl ? 1 : 0;
+                CK(cudaLaunchKernelEx(&cfg, jbf_upsample_gather_kernel<TW, TH>, p, g));
+                h->last_variant = 0x1000 | 0x400;
+                rc = KDME_OK;
+            }
+        }
+        if (rc != KDME_OK)
         switch (h->radius) {
 #define X(R) case R: rc = best_th == 16 ? launch_fast_rt<R, 16>(h, p, want_tma, rows, pdl)                     \
                         : best_th == 8 ? launch_fast_rt<R, 8>(h, p, want_tma, rows, pdl)                       \
@@ -721,10 +782,8 @@ static int ensure_pipe(jbf_handle* h, size_t bgr_step) {
     return KDME_OK;
 }
 
-extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const uint8_t* bgr_host, size_t bgr_step,
-                                float* out_host, int n_frames) {
-    if (!h || !depth_host || !bgr_host || !out_host) return fail(KDME_EINVAL, "jbf_process_host: NULL argument");
-    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_process_host: n_frames must be >= 1");
+static int process_host_impl(jbf_handle* h, const float* depth_host, const uint16_t* depth16_host,
+                             const uint8_t* bgr_host, size_t bgr_step, float* out_host, int n_frames) {
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
     if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "bgr step smaller than 3*width");
     DeviceGuard g(h->device);
@@ -732,18 +791,30 @@ extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const ui
     if (rc != KDME_OK) return rc;
     const size_t plane = (size_t)h->width * h->height;
     const size_t bgr_frame = bgr_step * h->height;
+    if (depth16_host)
+        for (int b = 0; b < kPipeDepth; b++)
+            if (!h->pipe_depth16[b]) CK(cudaMalloc(&h->pipe_depth16[b], plane * h->pipe_chunk * sizeof(uint16_t)));
     int chunk = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->pipe_chunk, ++chunk) {
         const int n = (n_frames - f0 < h->pipe_chunk) ? (n_frames - f0) : h->pipe_chunk;
         const int b = chunk % kPipeDepth;
         if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[b], 0));  // slot inputs consumed
-        CK(cudaMemcpyAsync(h->pipe_depth[b], depth_host + (size_t)f0 * plane, plane * n * sizeof(float),
-                           cudaMemcpyHostToDevice, h->s_h2d));
+        if (depth16_host)
+            CK(cudaMemcpyAsync(h->pipe_depth16[b], depth16_host + (size_t)f0 * plane, plane * n * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, h->s_h2d));
+        else
+            CK(cudaMemcpyAsync(h->pipe_depth[b], depth_host + (size_t)f0 * plane, plane * n * sizeof(float),
+                               cudaMemcpyHostToDevice, h->s_h2d));
         CK(cudaMemcpyAsync(h->pipe_bgr[b], bgr_host + (size_t)f0 * bgr_frame, bgr_frame * n, cudaMemcpyHostToDevice,
                            h->s_h2d));
         CK(cudaEventRecord(h->ev_in[b], h->s_h2d));
         CK(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
         if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->stream, h->ev_free[b], 0));  // slot output drained
+        if (depth16_host) {   // sensor millimetres -> float, as Buffer2D::insertData(xn::DepthMetaData*) does (Buffer2D.cpp:18-32)
+            const long long cnt = (long long)plane * n;
+            u16_to_f32_kernel<<<buf_blocks(cnt), 256, 0, h->stream>>>(h->pipe_depth16[b], h->pipe_depth[b], cnt);
+            CK(cudaGetLastError());
+        }
         rc = launch_presmooth(h, h->pipe_bgr[b], bgr_step, h->guide4, h->guide_pitch, n);
         if (rc != KDME_OK) return rc;
         rc = launch_filter(h, h->pipe_depth[b], h->guide4, h->guide_pitch, h->pipe_out[b], n, kStagePlain, nullptr, 0, 0, -1, 0,
@@ -759,6 +830,32 @@ extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const ui
     CK(cudaStreamSynchronize(h->stream));
     return KDME_OK;
 }
+
+extern "C" int jbf_process_host(jbf_handle* h, const float* depth_host, const uint8_t* bgr_host, size_t bgr_step,
+                                float* out_host, int n_frames) {
+    if (!h || !depth_host || !bgr_host || !out_host) return fail(KDME_EINVAL, "jbf_process_host: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_process_host: n_frames must be >= 1");
+    return process_host_impl(h, depth_host, nullptr, bgr_host, bgr_step, out_host, n_frames);
+}
+
+extern "C" int jbf_process_host_u16(jbf_handle* h, const uint16_t* depth_host, const uint8_t* bgr_host, size_t bgr_step,
+                                    float* out_host, int n_frames) {
+    if (!h || !depth_host || !bgr_host || !out_host) return fail(KDME_EINVAL, "jbf_process_host_u16: NULL argument");
+    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_process_host_u16: n_frames must be >= 1");
+    return process_host_impl(h, nullptr, depth_host, bgr_host, bgr_step, out_host, n_frames);
+}
+
+// Page-locked host memory for the buffers of jbf_process_host*: write-combined memory is read by the copy
+// engine without snooping the CPU caches (for buffers the CPU only writes, front to back: sensor frames);
+// the result buffer must be ordinary pinned memory (the CPU reads it).
+extern "C" void* kdme_host_alloc(size_t bytes, int write_combined) {
+    void* p = nullptr;
+    const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    cudaError_t e = cudaHostAlloc(&p, bytes, flags);
+    if (e != cudaSuccess) { fail(-(int)e, std::string("kdme_host_alloc: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+extern "C" void kdme_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" float* jbf_filtered_device(jbf_handle* h) { return h ? h->filtered_dev : nullptr; }
 
@@ -797,14 +894,16 @@ extern "C" const uint8_t* jbf_smooth_device(jbf_handle* h, size_t* step) {
     return h->smooth_bgr;
 }
 
-extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0xF00)) : -1; }
+extern "C" int jbf_kernel_variant(jbf_handle* h) { return h ? ((h->fast ? 0 : 1) | (h->last_variant & 0x1F00)) : -1; }
 
 // ------------------------------------------------------------------ MRF (next row f1)
 extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr_dev, size_t bgr_step, float* out_dev,
                        int window_radius, float color_sigma, float smooth_sigma) {
     if (!h || !depth_dev || !bgr_dev || !out_dev) return fail(KDME_EINVAL, "jbf_mrf: NULL argument");
     if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "jbf_mrf: bad radius");
+    if (depth_dev == out_dev) return fail(KDME_EINVAL, "jbf_mrf: in-place operation is not supported");
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
+    if (bgr_step < (size_t)3 * h->width) return fail(KDME_EINVAL, "jbf_mrf: bgr step smaller than 3*width");
     DeviceGuard g(h->device);
     dim3 blk(128), grd((h->width + 127) / 128, h->height, 1);
     bgr_to_guide4_kernel<<<grd, blk, 0, h->stream>>>(bgr_dev, (long long)bgr_step, 0, h->guide4, h->guide_pitch, 0,
@@ -882,6 +981,27 @@ extern "C" int kdme_mean_3d_error(const float* points_dev, const float* truth_de
 }
 
 // ------------------------------------------------------------------ guided fill
+template <int R>
+static int guided_launch_fast(const float* depth_dev, const float* depth_lo_dev, int wl, int hl, const int32_t* labels_dev,
+                              const uint8_t* bgr_dev, size_t bgr_step, float* out_dev, int width, int height,
+                              const std::vector<float>& lut, float sigma_color, float sigma_depth, cudaStream_t stream) {
+    constexpr int ws = 2 * R + 1;
+    GuidedFastParams<R> p;
+    for (int i = 0; i < ws * ws; i++)
+        p.ltab[i] = (lut[i] != 0.0f) ? (float)(std::log2((double)lut[i]) + (double)kWeightBias) : kWeightBias;
+    p.width = width; p.height = height;
+    p.depth = depth_dev; p.labels = labels_dev; p.bgr = bgr_dev; p.bgr_step = (long long)bgr_step; p.out = out_dev;
+    p.sigma_c = sigma_color;
+    p.nk0 = (float)(-kLog2e / (2.0 * (double)sigma_color * (double)sigma_color));
+    p.sq = sqrtf((float)kLog2e / (2.0f * sigma_depth * sigma_depth));
+    p.depth_lo = depth_lo_dev; p.wl = wl; p.hl = hl;
+    constexpr int TW = 32, TH = 8;
+    dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
+    guided_fill_fast_kernel<R, TW, TH><<<grd, TW * TH, 0, stream>>>(p);
+    CK(cudaGetLastError());
+    return KDME_OK;
+}
+
 static int guided_launch(const float* depth_dev, const float* depth_lo_dev, int wl, int hl, const int32_t* labels_dev,
                          const uint8_t* bgr_dev, size_t bgr_step, float* out_dev, int width, int height,
                          int window_radius, float sigma_spatial, float sigma_color, float sigma_depth, void* stream) {
@@ -890,6 +1010,17 @@ static int guided_launch(const float* depth_dev, const float* depth_lo_dev, int 
     const int ws = 2 * window_radius + 1;
     std::vector<float> lut;
     host_spatial_lut(lut, ws, sigma_spatial);
+    // fast form: compile-time window (3..7), sweep-1 colour guard cannot fire (expf(-3*255^2/(2 sc^2)) != 0)
+    const bool fast_ok = sigma_color != 0.0f && sigma_depth != 0.0f && !getenv("KDME_GUIDED_GENERIC") &&
+                         expf(-(float)(3 * 255 * 255) / (2 * (sigma_color * sigma_color))) != 0.0f;
+    if (fast_ok) {
+        switch (window_radius) {
+            case 1: return guided_launch_fast<1>(depth_dev, depth_lo_dev, wl, hl, labels_dev, bgr_dev, bgr_step, out_dev, width, height, lut, sigma_color, sigma_depth, (cudaStream_t)stream);
+            case 2: return guided_launch_fast<2>(depth_dev, depth_lo_dev, wl, hl, labels_dev, bgr_dev, bgr_step, out_dev, width, height, lut, sigma_color, sigma_depth, (cudaStream_t)stream);
+            case 3: return guided_launch_fast<3>(depth_dev, depth_lo_dev, wl, hl, labels_dev, bgr_dev, bgr_step, out_dev, width, height, lut, sigma_color, sigma_depth, (cudaStream_t)stream);
+            default: break;
+        }
+    }
     GuidedParams p;
     if (ws * ws > (int)(sizeof(p.spatial) / sizeof(float))) return fail(KDME_ENOTSUP, "guided fill: window too large");
     for (int i = 0; i < ws * ws; i++) p.spatial[i] = lut[i];
@@ -1009,14 +1140,11 @@ extern "C" int buf2d_update_u16_host(buf2d_handle* b, const uint16_t* depth_host
     if (!b || !depth_host) return fail(KDME_EINVAL, "buf2d_update_u16_host: NULL argument");
     DeviceGuard g(b->device);
     const long long n = (long long)b->width * b->height;
-    if (!b->scratch) CK(cudaMalloc(&b->scratch, n * sizeof(float)));
     if (!b->scratch16) CK(cudaMalloc(&b->scratch16, n * sizeof(uint16_t)));
     CK(cudaMemcpyAsync(b->scratch16, depth_host, n * sizeof(uint16_t), cudaMemcpyHostToDevice, b->stream));
-    u16_to_f32_kernel<<<buf_blocks(n * 4), 256, 0, b->stream>>>(b->scratch16, b->scratch, n);
+    buf2d_update_u16_kernel<<<buf_blocks(n), 256, 0, b->stream>>>(b->dw, b->scratch16, n);
     CK(cudaGetLastError());
-    int rc = buf_launch<kBufUpdate>(b, b->scratch, nullptr, 1);
-    if (rc != KDME_OK) return rc;
-    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaStreamSynchronize(b->stream));   // depth_host may be pageable: the caller may reuse it on return
     return KDME_OK;
 }
 extern "C" int buf2d_get_depth(buf2d_handle* b, float* out_dev) {

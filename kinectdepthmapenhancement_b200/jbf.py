@@ -193,14 +193,24 @@ class JointBilateralFilter:
         return out
 
     def process_host(self, depth_host: torch.Tensor, color_host: torch.Tensor, out_host: torch.Tensor):
-        """End-to-end with HOST tensors (ideally pinned): upload, Process, download; synchronous."""
-        for t, dt, nm in ((depth_host, torch.float32, "depth_host"), (color_host, torch.uint8, "color_host"),
+        """End-to-end with HOST tensors (ideally pinned, see host_buffer()): upload, Process, download;
+        synchronous.  depth_host may be float32 millimetres or uint16 millimetres (the sensor's format,
+        converted on the device)."""
+        if depth_host.dtype not in (torch.float32, torch.uint16, torch.int16):
+            raise TypeError("depth_host must be float32 or uint16")
+        for t, dt, nm in ((depth_host, depth_host.dtype, "depth_host"), (color_host, torch.uint8, "color_host"),
                           (out_host, torch.float32, "out_host")):
             if t.is_cuda or t.dtype != dt or not t.is_contiguous():
                 raise TypeError(f"{nm} must be a contiguous CPU tensor of {dt}")
         n = depth_host.shape[0]
-        _lib.check(_lib.lib().jbf_process_host(self._h, _ptr(depth_host), _ptr(color_host), 3 * self.width,
-                                               _ptr(out_host), n))
+        if tuple(depth_host.shape) != (n, self.height, self.width):
+            raise ValueError(f"depth_host must be [N, {self.height}, {self.width}]")
+        if tuple(color_host.shape) != (n, self.height, self.width, 3):
+            raise ValueError(f"color_host must be [{n}, {self.height}, {self.width}, 3]")
+        if tuple(out_host.shape) != (n, self.height, self.width):
+            raise ValueError(f"out_host must be [{n}, {self.height}, {self.width}]")
+        fn = _lib.lib().jbf_process_host if depth_host.dtype == torch.float32 else _lib.lib().jbf_process_host_u16
+        _lib.check(fn(self._h, _ptr(depth_host), _ptr(color_host), 3 * self.width, _ptr(out_host), n))
         return out_host
 
     def mrf(self, depth: torch.Tensor, color: torch.Tensor, window_radius=2, color_sigma=50.0, smooth_sigma=150.0):
@@ -215,6 +225,33 @@ class JointBilateralFilter:
     @property
     def kernel_variant(self) -> int:
         return _lib.lib().jbf_kernel_variant(self._h)
+
+
+class _HostBlock:
+    def __init__(self, nbytes: int, write_combined: bool):
+        self.ptr = _lib.lib().kdme_host_alloc(nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            _lib.check(_lib.KDME_EINVAL)
+        self.buf = (C.c_uint8 * nbytes).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            _lib.lib().kdme_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def host_buffer(shape, dtype: torch.dtype, write_combined: bool = False) -> torch.Tensor:
+    """Page-locked host tensor owned by the library (cudaHostAlloc): the buffers jbf_process_host expects.
+    write_combined=True for input buffers the CPU only fills front to back; never for results."""
+    n = 1
+    for s_ in shape:
+        n *= int(s_)
+    nbytes = max(1, n * torch.empty((), dtype=dtype).element_size())
+    blk = _HostBlock(nbytes, write_combined)
+    t = torch.frombuffer(blk.buf, dtype=dtype, count=n).view(*shape)
+    t._kdme_block = blk   # keeps the allocation alive as long as the tensor object
+    return t
 
 
 def _tensor_view(ptr: int, shape, dtype, device, owner):

@@ -41,14 +41,28 @@ def test_reference_arm_non_zero_rank_is_silent():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    line = _run(["--frames", "256", "--steps", "2", "--warmup", "3", "--e2e-frames", "128", "--cpu-seconds", "3"])
-    for k in REQUIRED + ["roofline", "cpu_baseline", "clocks"]:
+    line = _run(["--frames", "256", "--steps", "2", "--warmup", "3", "--e2e-frames", "128", "--cpu-seconds", "3",
+                 "--band-size", "2048"], timeout=900)
+    for k in REQUIRED + ["roofline", "cpu_baseline", "clocks", "parity", "extra", "e2e_u16"]:
         assert k in line, k
     rf = line["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in rf, k
     assert 0.3 < rf["frac"] < 1.2 and rf["hbm"]["frac"] < 0.1      # compute-bound stencil
-    assert line["gpu_launches"] == 2 * 2 * 4                        # 2 steps x (256/64 chunks) x 2 kernels
+    assert 0.3 < rf["mufu"]["frac"] < 1.05
+    assert line["gpu_launches"] == 2 * 4 * 3                        # 2 steps x (256/64 chunks) x (pre-smooth, filter, refine)
     assert line["e2e"]["h2d_bytes_per_step"] == 128 * 640 * 480 * 7 and line["e2e"]["d2h_bytes_per_step"] == 128 * 640 * 480 * 4
+    assert line["e2e_u16"]["h2d_bytes_per_step"] == 128 * 640 * 480 * 5
     assert line["scaling"] == "weak" and line["vs_baseline"] is None and line["dtype"] == "f32"
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    # parity block: the north_star tolerance, flat, on the configs[1] stream and on configs[0]
+    par = line["parity"]
+    assert par["mask_mismatches"] == 0 and par["presmooth_bit_exact"] is True
+    assert par["max_abs_regular_mm"] <= 1e-3 and par["config1"]["max_abs_regular_mm"] <= 1e-3
+    assert par["frames_checked"] >= 4 and par["refine_queue_dropped"] == 0
+    ex = line["extra"]
+    assert ex["bands_nccl"]["seam_rows_bitwise_equal_single_gpu_path"] is True
+    assert ex["bands_nccl"]["oracle_seam_check"]["mask_mismatches"] == 0
+    assert ex["bands_nccl"]["oracle_seam_check"]["max_abs_regular_mm"] <= 1e-3
+    assert ex["single_frame"]["r7_us"] > 0 and ex["upsample"]["ms"] > 0 and len(ex["sweep"]["rows"]) == 13
+    assert ex["strong"]["scaling"] == "strong"

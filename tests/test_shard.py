@@ -153,3 +153,40 @@ def test_peer_memory_halos_equal_whole_frame_bit_for_bit(w, h, radius, world):
         got[p.y0:p.y1] = rb.process_peer(barrier=False, pointers=(d_up, d_dn, b_up, b_dn)).cpu()
     assert not torch.isnan(got).any()
     assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+def _two_rank_worker(rank, world, port, size, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from tools import workloads
+    out = {}
+    for mode in ("nccl", "peer"):
+        out[mode] = workloads.bands(size, 9, peer=(mode == "peer"), steps=1, oracle_cols=256)
+    if rank == 0:
+        q.put(out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one NVLink box (gpurun --gpus 2)")
+def test_real_two_rank_bands_nccl_and_peer_memory():
+    """The real thing on two GPUs: NCCL send/recv halos and in-kernel peer-memory halos.  Every rank re-filters
+    the rows on both sides of the seam without band logic (bit for bit), rank 0 checks the two seam rows against
+    the fp64 CPU oracle."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, 29517, 2048, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for mode in ("nccl", "peer"):
+        r = res[mode]
+        assert r["seam_rows_bitwise_equal_single_gpu_path"] is True, mode
+        assert r["oracle_seam_check"]["mask_mismatches"] == 0 and r["oracle_seam_check"]["max_abs_regular_mm"] <= 1e-3
+    assert res["nccl"]["band_digests"] == res["peer"]["band_digests"]
