@@ -13,10 +13,19 @@
 
 #include "kdme_b200.h"
 
-#ifndef __CUDACC__
-#ifndef KDME_HAVE_FLOAT2
-struct kdme_float2 { float x, y; };
+/* float2: the CUDA vector type when <vector_types.h> is reachable (any CUDA toolkit include path), else an
+ * identical plain struct, so that insertData(float2*) -- Buffer2D.h:24 -- keeps its reference spelling. */
+#if defined(__CUDACC__) || defined(__VECTOR_TYPES_H__)
+#define KDME_FLOAT2 float2
+#elif defined(__has_include)
+#if __has_include(<vector_types.h>)
+#include <vector_types.h>
+#define KDME_FLOAT2 float2
 #endif
+#endif
+#ifndef KDME_FLOAT2
+struct float2 { float x, y; };
+#define KDME_FLOAT2 float2
 #endif
 
 class ArrayBuffer {
@@ -50,7 +59,8 @@ public:
     virtual void getWeightMap(float* out) { check(buf2d_get_weight(b_, out)); }                       /* Buffer2D.cu:91-94 */
     virtual void updateData(float* data) { check(buf2d_update_f32(b_, data)); }                       /* Buffer2D.cu:116-120 */
     void updateData(float* data, int n_frames) { check(buf2d_update_batch_f32(b_, data, n_frames)); }
-    template <class Float2> void insertData2(Float2* data) { check(buf2d_insert_f32x2(b_, reinterpret_cast<float*>(data))); } /* Buffer2D.cu:144-147 */
+    void insertData(KDME_FLOAT2* data) { check(buf2d_insert_f32x2(b_, reinterpret_cast<float*>(data))); }     /* Buffer2D.h:24, Buffer2D.cu:123-147 */
+    template <class Float2> void insertData2(Float2* data) { check(buf2d_insert_f32x2(b_, reinterpret_cast<float*>(data))); } /* same, any {x,y} pair type */
     void insertData(const uint16_t* host_depth) { check(buf2d_update_u16_host(b_, host_depth)); }     /* Buffer2D.cpp:18-32 */
 private:
     Buffer2D(const Buffer2D&);

@@ -67,6 +67,17 @@ public:
                       int n_frames) {
         check(jbf_process_batch(h_, depth_device, bgr_device, bgr_step, out_device, n_frames));
     }
+    /* Process + DimensionConvertor::projectiveToReal fused (main.cpp:179 + :182): xyz_device = float3[W*H]. */
+    void ProcessXYZ(float* depth_device, cv::gpu::GpuMat color_image, float* xyz_device, float fx, float fy, int cx, int cy) {
+        check(jbf_process_xyz(h_, depth_device, color_image.data, color_image.step, xyz_device, fx, fy, cx, cy));
+    }
+    /* Host buffers end to end; uint16 depth is the sensor's own format (main.cpp:91-95). */
+    void ProcessHost(const float* depth_host, const unsigned char* bgr_host, size_t bgr_step, float* out_host, int n_frames) {
+        check(jbf_process_host(h_, depth_host, bgr_host, bgr_step, out_host, n_frames));
+    }
+    void ProcessHost(const unsigned short* depth_host, const unsigned char* bgr_host, size_t bgr_step, float* out_host, int n_frames) {
+        check(jbf_process_host_u16(h_, depth_host, bgr_host, bgr_step, out_host, n_frames));
+    }
     float* getFiltered_Device() const { return jbf_filtered_device(h_); }                       /* .cpp:41-43 */
     float* getFiltered_Host() const { return const_cast<float*>(jbf_filtered_host(h_)); }        /* .cpp:44-46 */
     cv::gpu::GpuMat getSmoothImage_Device() {                                                    /* .cpp:47-49 */

@@ -792,12 +792,30 @@ __device__ __forceinline__ double exp_neg_f64(double x) {
 // KMAX = taps per lane the instantiation can hold: (2r+1)^2 <= 32 * KMAX
 template <int KMAX>
 __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, const int radius) {
-    grid_dependency_wait();   // the queue is complete only when the filter kernel has finished
     const int lane = threadIdx.x & 31;
+    const int ws = 2 * radius + 1, ntap = ws * ws;
+    // the lane's taps t = lane + 32 u -> window offsets and spatial weights, once per warp (not per pixel)
+    int tdx[KMAX], tdy[KMAX];
+    double tsw[KMAX];
+    {
+        int ti = lane / ws, tj = lane - ti * ws;
+        const int di = 32 / ws, dj = 32 - di * ws;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int t = lane + 32 * u;
+            tdx[u] = tj - radius;
+            tdy[u] = (t < ntap) ? ti - radius : (1 << 28);    // beyond the window: fails the bounds test below
+            const float s = (t < ntap) ? __ldg(p.slut + t) : 0.f;
+            tsw[u] = (s != 0.0f) ? (double)s : 1.0;           // skip-if-zero guard on the spatial factor (.cu:30-31)
+            ti += di; tj += dj;
+            if (tj >= ws) { tj -= ws; ++ti; }
+        }
+    }
+    grid_dependency_wait();   // the queue is complete only when the filter kernel has finished
     const unsigned pushed = *reinterpret_cast<volatile unsigned int*>(p.q_count);
     const unsigned count = pushed < p.q_capacity ? pushed : p.q_capacity;
-    const int ws = 2 * radius + 1, ntap = ws * ws;
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool plain = (p.mode != kStageUpsample) && p.depth_up == nullptr && p.depth_dn == nullptr;
     for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < count; item += nwarps) {
         const unsigned idx = p.q_items[item];
         const unsigned per_frame = (unsigned)p.out_rows * (unsigned)p.width;
@@ -806,32 +824,26 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
         const int oy = (int)(rem / (unsigned)p.width), x = (int)(rem - (unsigned)oy * (unsigned)p.width);
         const int y = oy + p.y_off;
         const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
+        const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
         const uint32_t gpix = __ldg(gsrc + (long long)y * p.guide_pitch + x);
         // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight
         double dl[KMAX], fl[KMAX];
         double a = 0.0, wt = 0.0;
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
-            const int t = lane + 32 * u;
+            const int ty = y + tdy[u], tx = x + tdx[u];
             dl[u] = 0.0;
             fl[u] = 0.0;
-            if (t < ntap) {
-                const int i = t / ws, j = t - i * ws;
-                const int ty = y + i - radius, tx = x + j - radius;
-                if (tx >= 0 && tx < p.width && ty >= 0 && ty < p.height) {
-                    const float df = jbf_sample_depth(p, frame, tx, ty);
-                    if (df > kValidDepth) {
-                        const uint32_t ad = __vabsdiffu4(gpix, __ldg(gsrc + (long long)ty * p.guide_pitch + tx));
-                        const double cd = (double)__dp4a(ad, ad, 0u);
-                        double f = 1.0;
-                        const float s = __ldg(p.slut + t);
-                        if (s != 0.0f) f *= (double)s;
-                        f *= exp_neg_f64(cd * p.kc);
-                        dl[u] = (double)df;
-                        fl[u] = f;
-                        a += dl[u] * f;
-                        wt += f;
-                    }
+            if (tx >= 0 && tx < p.width && ty >= 0 && ty < p.height) {
+                const float df = plain ? __ldg(dsrc + (long long)ty * p.width + tx) : jbf_sample_depth(p, frame, tx, ty);
+                if (df > kValidDepth) {
+                    const uint32_t ad = __vabsdiffu4(gpix, __ldg(gsrc + (long long)ty * p.guide_pitch + tx));
+                    const double cd = (double)__dp4a(ad, ad, 0u);
+                    const double f = tsw[u] * exp_neg_f64(cd * p.kc);
+                    dl[u] = (double)df;
+                    fl[u] = f;
+                    a += dl[u] * f;
+                    wt += f;
                 }
             }
         }

@@ -11,7 +11,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/kdme_b200.h"
@@ -56,16 +59,37 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
+    });
     return fn;
+}
+
+// The handle-less entry points (kdme_guided_*, kdme_depth_bilateral_xyz, kdme_mean_3d_error,
+// kdme_projective_to_real) launch on the CURRENT device: their pointers must live there.
+static int check_pointer_device(const void* ptr, const char* who) {
+    cudaPointerAttributes a;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) return fail(KDME_EINVAL, std::string(who) + ": no current CUDA device");
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return fail(KDME_EINVAL, std::string(who) + ": not a CUDA pointer"); }
+    if (a.type == cudaMemoryTypeDevice && a.device != cur)
+        return fail(KDME_EINVAL, std::string(who) + ": pointer lives on device " + std::to_string(a.device) +
+                                 " but the current device is " + std::to_string(cur) + " (call cudaSetDevice first)");
+    static std::atomic<unsigned long long> ok_devs{0}, bad_devs{0};   // compute capability, looked up once per device
+    const unsigned long long bit = 1ull << (cur & 63);
+    if (!((ok_devs.load(std::memory_order_acquire) | bad_devs.load(std::memory_order_acquire)) & bit)) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cur);
+        (major == 10 ? ok_devs : bad_devs).fetch_or(bit, std::memory_order_release);
+    }
+    if (bad_devs.load(std::memory_order_acquire) & bit)
+        return fail(KDME_ENOTSUP, std::string(who) + ": this library is built for sm_100a (B200) only");
+    return KDME_OK;
 }
 
 // 3-D map over [n][rows][pitch_elems] 4-byte elements, box {bx, by, 1}, zero OOB fill.
@@ -379,9 +403,9 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
         p.ksize = h->ps_ksize; p.space_lut = h->ps_space_dev; p.color_lut = h->ps_color_dev;
         p.bgr_up = bgr_up; p.bgr_dn = bgr_dn; p.band0 = band0; p.band1 = band1;
         if (h->ps_ksize == 5) {
-            constexpr int TW = 64, TH = 8;
+            constexpr int TW = 64, TH = 16;
             dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
-            presmooth5_kernel<TW, TH><<<grd, (TW / 4) * TH, 0, h->stream>>>(p);
+            presmooth5_kernel<TW, TH><<<grd, (TW / 4) * (TH / 2), 0, h->stream>>>(p);
         } else {
             constexpr int TW = 32, TH = 8;
             dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
@@ -577,7 +601,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
             // launch latency hides behind the filter (it waits for the filter's completion on the device)
             if (p.mode == kStageTma) p.mode = kStagePlain;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(148 * 4);
+            cfg.gridDim = dim3(148 * 5);
             cfg.blockDim = dim3(128);
             cfg.stream = h->stream;
             cudaLaunchAttribute attr[1];
@@ -628,7 +652,8 @@ extern "C" int jbf_presmooth(jbf_handle* h, const uint8_t* bgr_dev, size_t bgr_s
 extern "C" int jbf_filter_guide4(jbf_handle* h, const float* depth_dev, const uint8_t* guide4_dev, size_t guide_step,
                                  float* out_dev, int n_frames) {
     if (!h || !depth_dev || !guide4_dev || !out_dev) return fail(KDME_EINVAL, "jbf_filter_guide4: NULL argument");
-    if (n_frames < 1) return fail(KDME_EINVAL, "jbf_filter_guide4: n_frames must be >= 1");
+    if (n_frames < 1 || n_frames > 65535) return fail(KDME_EINVAL, "jbf_filter_guide4: n_frames must be in [1, 65535] (frames are grid.z of one launch)");
+    if (depth_dev == out_dev) return fail(KDME_EINVAL, "jbf_filter_guide4: in-place operation is not supported");
     if (guide_step == 0) guide_step = (size_t)h->guide_pitch * 4;
     if (guide_step % 4 != 0 || guide_step < (size_t)h->width * 4)
         return fail(KDME_EINVAL, "jbf_filter_guide4: guide_step must be a multiple of 4 and >= 4*width");
@@ -922,6 +947,7 @@ extern "C" int jbf_mrf(jbf_handle* h, const float* depth_dev, const uint8_t* bgr
 extern "C" int kdme_projective_to_real(const float* depth_dev, float* xyz_dev, int width, int height, float fx,
                                        float fy, int cx, int cy, void* stream) {
     if (!depth_dev || !xyz_dev || width <= 0 || height <= 0) return fail(KDME_EINVAL, "projective_to_real: bad argument");
+    { int rcd = check_pointer_device(depth_dev, "kdme_projective_to_real"); if (rcd != KDME_OK) return rcd; }
     const long long n = (long long)width * height;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -938,16 +964,32 @@ extern "C" int kdme_depth_bilateral_xyz(const float* normalized_dev, const float
     if (in_dev == out_dev) return fail(KDME_EINVAL, "kdme_depth_bilateral_xyz: in-place operation is not supported");
     if (width <= 0 || height <= 0 || window_radius < 0 || window_radius > KDME_MAX_RADIUS || !(sigma_depth > 0))
         return fail(KDME_EINVAL, "kdme_depth_bilateral_xyz: bad size, radius or sigma");
+    int rcd = check_pointer_device(in_dev, "kdme_depth_bilateral_xyz");
+    if (rcd != KDME_OK) return rcd;
     const int ws = 2 * window_radius + 1;
-    std::vector<float> lut;
-    host_spatial_lut(lut, ws, sigma_spatial);
-    std::vector<float> l2(lut.size());
-    for (size_t i = 0; i < lut.size(); i++) l2[i] = (lut[i] > 0.f) ? (float)std::log2((double)lut[i]) : -1.0e30f;
-    float* ltab = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMallocAsync(&ltab, l2.size() * sizeof(float), st));
-    CK(cudaMemcpyAsync(ltab, l2.data(), l2.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // l2 is a stack-lifetime host buffer
+    // log2-domain spatial LUT, cached per (device, window, sigma): built and uploaded once
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, float>, float*> cache;
+    float* ltab = nullptr;
+    {
+        int cur = 0;
+        CK(cudaGetDevice(&cur));
+        std::lock_guard<std::mutex> lk(mu);
+        auto key = std::make_tuple(cur, ws, sigma_spatial);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            std::vector<float> lut;
+            host_spatial_lut(lut, ws, sigma_spatial);
+            std::vector<float> l2(lut.size());
+            for (size_t i = 0; i < lut.size(); i++) l2[i] = (lut[i] > 0.f) ? (float)std::log2((double)lut[i]) : -1.0e30f;
+            CK(cudaMalloc(&ltab, l2.size() * sizeof(float)));
+            CK(cudaMemcpy(ltab, l2.data(), l2.size() * sizeof(float), cudaMemcpyHostToDevice));
+            cache[key] = ltab;
+        } else {
+            ltab = it->second;
+        }
+    }
     constexpr int TW = 32, TH = 8;
     const int SP = TW + 2 * window_radius, SH = TH + 2 * window_radius;
     dim3 grd((width + TW - 1) / TW, (height + TH - 1) / TH);
@@ -955,7 +997,6 @@ extern "C" int kdme_depth_bilateral_xyz(const float* normalized_dev, const float
         normalized_dev, in_dev, out_dev, ltab, width, height, window_radius,
         (float)(-kLog2e / (2.0 * (double)sigma_depth * (double)sigma_depth)));
     CK(cudaGetLastError());
-    CK(cudaFreeAsync(ltab, st));
     return KDME_OK;
 }
 
@@ -963,6 +1004,7 @@ extern "C" int kdme_mean_3d_error(const float* points_dev, const float* truth_de
                                   double* mean_out, long long* count_out, void* stream) {
     if (!points_dev || !truth_dev || !mean_out || n_points <= 0)
         return fail(KDME_EINVAL, "kdme_mean_3d_error: bad argument");
+    { int rcd = check_pointer_device(points_dev, "kdme_mean_3d_error"); if (rcd != KDME_OK) return rcd; }
     cudaStream_t st = (cudaStream_t)stream;
     double* acc = nullptr;
     CK(cudaMallocAsync(&acc, 2 * sizeof(double), st));
@@ -1043,6 +1085,7 @@ extern "C" int kdme_guided_fill(const float* depth_dev, const int32_t* labels_de
     if (width <= 0 || height <= 0) return fail(KDME_EINVAL, "kdme_guided_fill: bad size");
     if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "kdme_guided_fill: bad radius");
     if (depth_dev == out_dev) return fail(KDME_EINVAL, "kdme_guided_fill: in-place operation is not supported");
+    { int rcd = check_pointer_device(depth_dev, "kdme_guided_fill"); if (rcd != KDME_OK) return rcd; }
     return guided_launch(depth_dev, nullptr, 0, 0, labels_dev, bgr_dev, bgr_step, out_dev, width, height, window_radius,
                          sigma_spatial, sigma_color, sigma_depth, stream);
 }
@@ -1055,6 +1098,7 @@ extern "C" int kdme_guided_upsample(const float* depth_lo_dev, int wl, int hl, c
     if (width <= 0 || height <= 0 || wl <= 0 || hl <= 0 || wl > width || hl > height)
         return fail(KDME_EINVAL, "kdme_guided_upsample: low-res size must be positive and <= the high-res size");
     if (window_radius < 0 || window_radius > KDME_MAX_RADIUS) return fail(KDME_EINVAL, "kdme_guided_upsample: bad radius");
+    { int rcd = check_pointer_device(depth_lo_dev, "kdme_guided_upsample"); if (rcd != KDME_OK) return rcd; }
     return guided_launch(nullptr, depth_lo_dev, wl, hl, labels_hi_dev, bgr_hi_dev, bgr_step, out_hi_dev, width, height,
                          window_radius, sigma_spatial, sigma_color, sigma_depth, stream);
 }

@@ -107,9 +107,10 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
 // planes so a thread fetches its 8-column row segment with conflict-free 16-byte LDS; a tap is then
 // VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
 template <int TW, int TH>
-__global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const PresmoothParams p) {
+__global__ void __launch_bounds__((TW / 4) * (TH / 2)) presmooth5_kernel(const PresmoothParams p) {
     grid_launch_dependents();   // PDL: the filter's prologue (LUTs, descriptors, barrier) may start now
-    constexpr int NT = (TW / 4) * TH, R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
+    static_assert(TH % 2 == 0, "a thread owns two rows");
+    constexpr int NT = (TW / 4) * (TH / 2), R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
     constexpr int XO = 4 - R;                                               // first used column of a staged row
     __shared__ __align__(16) float sB[SP * SH];
     __shared__ __align__(16) float sG[SP * SH];
@@ -153,20 +154,25 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
     if (tid < 25) sSp[tid] = __ldg(p.space_lut + tid);
     __syncthreads();
 
-    const int lx = tid % (TW / 4), ly = tid / (TW / 4);
-    uint32_t c[4];
-    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f},
-          ws[4] = {0.f, 0.f, 0.f, 0.f};
-    {
-        const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (ly + R) * SP + 4 * lx + 4);
-        c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+    // each thread owns a 4 x 2 block of pixels: a staged row segment is fetched once and serves the taps of
+    // both output rows (6 row fetches per 8 pixels instead of 10 -- the kernel is bound by shared-memory
+    // wavefronts).  Per pixel the taps are still visited dy-major, dx-minor: same sums, same bits.
+    const int lx = tid % (TW / 4), ly = tid / (TW / 4);   // ly indexes PAIRS of rows
+    uint32_t c[2][4];
+    float s0[2][4], s1[2][4], s2[2][4], ws[2][4];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (2 * ly + o + R) * SP + 4 * lx + 4);
+        c[o][0] = c4.x; c[o][1] = c4.y; c[o][2] = c4.z; c[o][3] = c4.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s0[o][k] = 0.f; s1[o][k] = 0.f; s2[o][k] = 0.f; ws[o][k] = 0.f; }
     }
 #pragma unroll
-    for (int dy = 0; dy < 5; ++dy) {
+    for (int sr = 0; sr < 6; ++sr) {
         // columns [4*lx, 4*lx + 12) of the staged row: pixel k, tap dx sits at local column XO + k + dx
         float rb[12], rg[12], rr[12];
         uint32_t rp[12];
-        const int base = (ly + dy) * SP + 4 * lx;
+        const int base = (2 * ly + sr) * SP + 4 * lx;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             const float4 b4 = *reinterpret_cast<const float4*>(sB + base + 4 * v);
@@ -179,39 +185,49 @@ __global__ void __launch_bounds__((TW / 4) * TH) presmooth5_kernel(const Presmoo
             rp[4 * v] = p4.x; rp[4 * v + 1] = p4.y; rp[4 * v + 2] = p4.z; rp[4 * v + 3] = p4.w;
         }
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx) {
-            if ((dx - 2) * (dx - 2) + (dy - 2) * (dy - 2) > 4) continue;  // outside the circle (compile time)
-            const float sw = sSp[dy * 5 + dx];
+        for (int o = 0; o < 2; ++o) {
+            const int dy = sr - o;
+            if (dy < 0 || dy > 4) continue;   // compile time
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = XO + k + dx;
-                const uint32_t ad = __vabsdiffu4(rp[col], c[k]);
-                const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
-                const float w = __fmul_rn(sw, sCol[l1]);
-                s0[k] = __fmaf_rn(w, rb[col], s0[k]);
-                s1[k] = __fmaf_rn(w, rg[col], s1[k]);
-                s2[k] = __fmaf_rn(w, rr[col], s2[k]);
-                ws[k] = __fadd_rn(ws[k], w);
+            for (int dx = 0; dx < 5; ++dx) {
+                if ((dx - 2) * (dx - 2) + (dy - 2) * (dy - 2) > 4) continue;  // outside the circle (compile time)
+                const float sw = sSp[dy * 5 + dx];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int col = XO + k + dx;
+                    const uint32_t ad = __vabsdiffu4(rp[col], c[o][k]);
+                    const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
+                    const float w = __fmul_rn(sw, sCol[l1]);
+                    s0[o][k] = __fmaf_rn(w, rb[col], s0[o][k]);
+                    s1[o][k] = __fmaf_rn(w, rg[col], s1[o][k]);
+                    s2[o][k] = __fmaf_rn(w, rr[col], s2[o][k]);
+                    ws[o][k] = __fadd_rn(ws[o][k], w);
+                }
             }
         }
     }
-    const int gy = y0 + ly, gx = x0 + 4 * lx;
-    if (gy >= p.height || gx >= p.width) return;
-    uint32_t o[4];
+    const int gx = x0 + 4 * lx;
+    if (gx >= p.width) return;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0[k], ws[k])), 0.f), 255.f);
-        const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1[k], ws[k])), 0.f), 255.f);
-        const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2[k], ws[k])), 0.f), 255.f);
-        o[k] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
-    }
-    uint32_t* dst = p.guide4 + (long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx;
-    if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
+    for (int o = 0; o < 2; ++o) {
+        const int gy = y0 + 2 * ly + o;
+        if (gy >= p.height) continue;
+        uint32_t ov[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (gx + k < p.width) dst[k] = o[k];
+        for (int k = 0; k < 4; ++k) {
+            const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0[o][k], ws[o][k])), 0.f), 255.f);
+            const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1[o][k], ws[o][k])), 0.f), 255.f);
+            const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2[o][k], ws[o][k])), 0.f), 255.f);
+            ov[k] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
+        }
+        uint32_t* dst = p.guide4 + (long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx;
+        if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (gx + k < p.width) dst[k] = ov[k];
+        }
     }
 }
 

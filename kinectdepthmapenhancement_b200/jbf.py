@@ -182,12 +182,23 @@ class JointBilateralFilter:
         return g4
 
     def filter_guide4(self, depth: torch.Tensor, guide4: torch.Tensor, out: torch.Tensor | None = None):
-        """Filter only, on an already smoothed internal guide (see presmooth())."""
+        """Filter only, on an already smoothed internal guide (see presmooth()): depth [N,H,W] f32,
+        guide4 [N,H,pitch] int32 words {B,G,R,0} with pitch >= W and a multiple of 4."""
         _check_cuda(depth, torch.float32, "depth", self.device)
         _check_cuda(guide4, torch.int32, "guide4", self.device)
+        if depth.dim() != 3 or tuple(depth.shape[1:]) != (self.height, self.width):
+            raise ValueError(f"depth must be [N, {self.height}, {self.width}]")
         n = depth.shape[0]
+        if guide4.dim() != 3 or guide4.shape[0] != n or guide4.shape[1] != self.height or \
+                guide4.shape[2] < self.width or guide4.shape[2] % 4:
+            raise ValueError(f"guide4 must be [{n}, {self.height}, pitch] with pitch >= {self.width} and a multiple of 4")
         if out is None:
             out = torch.empty_like(depth)
+        _check_cuda(out, torch.float32, "out", self.device)
+        if tuple(out.shape) != tuple(depth.shape):
+            raise ValueError("out must have the shape of depth")
+        if out.data_ptr() == depth.data_ptr():
+            raise ValueError("in-place filtering is not supported")
         _lib.check(_lib.lib().jbf_filter_guide4(self._h, _ptr(depth), _ptr(guide4), guide4.shape[-1] * 4,
                                                 _ptr(out), n))
         return out
@@ -217,6 +228,8 @@ class JointBilateralFilter:
         """MarkovRandomField::Process -- MarkovRandomField.cu:4-49 (next row f1)."""
         _check_cuda(depth, torch.float32, "depth", self.device)
         _check_cuda(color, torch.uint8, "color", self.device)
+        if tuple(depth.shape) != (self.height, self.width) or tuple(color.shape) != (self.height, self.width, 3):
+            raise ValueError(f"depth must be [{self.height}, {self.width}] and color [{self.height}, {self.width}, 3]")
         out = torch.empty_like(depth)
         _lib.check(_lib.lib().jbf_mrf(self._h, _ptr(depth), _ptr(color), 3 * self.width, _ptr(out),
                                       window_radius, color_sigma, smooth_sigma))

@@ -18,6 +18,12 @@ int run(float* inputDepth_Device, cv::gpu::GpuMat Color_Device, float* bufferDep
     JBF.Process(inputDepth_Device, Color_Device);
     float* filtered = JBF.getFiltered_Device();
     cv::gpu::GpuMat smooth = JBF.getSmoothImage_Device();
+    float2* xy = 0;
+    Buffer.insertData(xy);                       // Buffer2D.h:24 insertData(float2*), reference spelling
+    ArrayBuffer::weighted_d* dw = Buffer.getRawPointer();
+    Buffer.insertData(dw);                       // Buffer2D.h:23
+    float* cloud = 0;
+    JBF.ProcessXYZ(inputDepth_Device, Color_Device, cloud, 525.f, 525.f, W / 2, H / 2);   // main.cpp:179 + :182 fused
     return filtered != 0 && smooth.data != 0;
 }
 int main() {

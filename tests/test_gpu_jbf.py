@@ -431,3 +431,71 @@ def test_mrf_and_projective_to_real():
     assert np.abs(out - want).max() <= 2e-3
     xyz = projective_to_real(torch.from_numpy(depth).cuda(), 525.0, 525.0, 80, 60).cpu().numpy()
     assert np.array_equal(xyz.view(np.uint32), oracle.projective_to_real(depth, 525.0, 525.0, 80, 60).view(np.uint32))
+
+
+def test_process_xyz_equals_projective_to_real_of_filtered():
+    """f3 as SURVEY 8(f) asks: back-projection fused into the filter epilogue (main.cpp:179 + :182 as one launch
+    pair) is bit-identical to projectiveToReal(filtered) -- also on the pixels re-evaluated in fp64."""
+    from kinectdepthmapenhancement_b200 import projective_to_real, synth
+    for (w, h, r) in [(640, 480, 7), (322, 241, 2), (70, 50, 3)]:
+        depth, bgr = synth.rgbd_frame(w, h, seed=8, frame=0, device="cuda")
+        f = _jbf_cls()(w, h, window_radius=r)
+        xyz = f.process_xyz(depth, bgr, 525.0, 520.0, w // 2, h // 2)
+        filt = f.getFiltered_Device().clone()
+        f.Process(depth, bgr)
+        assert torch.equal(filt.view(torch.int32), f.getFiltered_Device().view(torch.int32))
+        want = projective_to_real(filt, 525.0, 520.0, w // 2, h // 2)
+        assert torch.equal(xyz.view(torch.int32), want.view(torch.int32))
+        assert np.array_equal(want.cpu().numpy().view(np.uint32),
+                              oracle.projective_to_real(filt.cpu().numpy(), 525.0, 520.0, w // 2, h // 2).view(np.uint32))
+
+
+def test_process_host_u16_and_library_pinned_buffers():
+    """Sensor-format depth (uint16 mm) uploaded and converted on the device == the float path on the same
+    integers; buffers from kdme_host_alloc (plain and write-combined)."""
+    from kinectdepthmapenhancement_b200 import synth
+    from kinectdepthmapenhancement_b200.jbf import host_buffer
+    n, w, h = 5, 160, 120
+    depth, bgr = synth.rgbd_stream(n, w, h, seed=4)
+    d_int = depth.round().clamp_(0, 65535)
+    f = _jbf_cls()(w, h, window_radius=3, max_batch=2)
+    want = f.process_batch(d_int.cuda(), bgr.cuda()).cpu()
+    for wc in (False, True):
+        dh = host_buffer((n, h, w), torch.int16, write_combined=wc)
+        ch = host_buffer((n, h, w, 3), torch.uint8, write_combined=wc)
+        oh = host_buffer((n, h, w), torch.float32)
+        dh.copy_(d_int.to(torch.int32).to(torch.int16))
+        ch.copy_(bgr)
+        f.process_host(dh, ch, oh)
+        assert torch.equal(oh, want)
+    with pytest.raises(ValueError):
+        f.process_host(torch.zeros((n, h, w)), torch.zeros((n - 1, h, w, 3), dtype=torch.uint8), torch.zeros((n, h, w)))
+
+
+def test_refine_stats_and_queue():
+    """Ill-conditioned pixels are counted; a frame of one flat surface has none."""
+    depth, bgr = synth_np(320, 240, seed=8, frame=0)
+    f = _jbf_cls()(320, 240, window_radius=7)
+    f.Process(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda())
+    refined, dropped = f.refine_stats()
+    assert refined > 0 and dropped == 0
+    flat = np.full((240, 320), 1500.0, np.float32)
+    f.Process(torch.from_numpy(flat).cuda(), torch.from_numpy(bgr).cuda())
+    assert f.refine_stats() == (0, 0)
+
+
+def test_filter_guide4_rejects_mismatched_tensors():
+    f = _jbf_cls()(64, 48, window_radius=2)
+    d = torch.zeros((2, 48, 64), device="cuda")
+    g = torch.zeros((2, 48, 64), dtype=torch.int32, device="cuda")
+    f.filter_guide4(d, g)
+    with pytest.raises(ValueError):
+        f.filter_guide4(d, g[:1])
+    with pytest.raises(ValueError):
+        f.filter_guide4(d, torch.zeros((2, 48, 62), dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        f.filter_guide4(d, g, out=torch.zeros((1, 48, 64), device="cuda"))
+    with pytest.raises(ValueError):
+        f.filter_guide4(d, g, out=d)
+    with pytest.raises(ValueError):
+        f.filter_guide4(torch.zeros((2, 48, 32), device="cuda"), g)
