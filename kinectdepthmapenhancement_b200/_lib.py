@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkdme_b200.so")
+# KDME_LIB_PATH: A/B runs of two builds of the library on the same GPU box (development only)
+LIB_PATH = os.environ.get("KDME_LIB_PATH") or os.path.join(_HERE, "libkdme_b200.so")
 
 KDME_OK = 0
 KDME_EINVAL = -100001

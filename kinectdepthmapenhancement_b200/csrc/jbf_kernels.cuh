@@ -753,6 +753,18 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
+// two sums reduced in lockstep (their shuffles interleave: half the latency of two separate reductions)
+__device__ __forceinline__ void warp_sum2_f64(double& a, double& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+        a += ta;
+        b += tb;
+    }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
+}
+
 __device__ __forceinline__ float jbf_sample_depth(const JbfParams& p, int frame, int gx, int gy) {
     if (p.mode == kStageUpsample) {
         const int xl = upsample_site(gx, p.width, p.wl), yl = upsample_site(gy, p.height, p.hl);
@@ -812,12 +824,20 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
         }
     }
     grid_dependency_wait();   // the queue is complete only when the filter kernel has finished
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const unsigned first = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned total_px = (unsigned)p.out_rows * (unsigned)p.width * (unsigned)p.n_frames;
+    // the count and this warp's first item are fetched together (one round trip); a slot beyond the count holds a
+    // stale index, which is clamped into the frame and never used
+    unsigned idx_next = (first < p.q_capacity) ? p.q_items[first] : 0u;
     const unsigned pushed = *reinterpret_cast<volatile unsigned int*>(p.q_count);
     const unsigned count = pushed < p.q_capacity ? pushed : p.q_capacity;
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
     const bool plain = (p.mode != kStageUpsample) && p.depth_up == nullptr && p.depth_dn == nullptr;
-    for (unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < count; item += nwarps) {
-        const unsigned idx = p.q_items[item];
+    const int tc = radius * ws + radius;   // the centre tap: lane tc % 32 holds the centre's guide word in slot tc / 32
+    for (unsigned item = first; item < count; item += nwarps) {
+        unsigned idx = idx_next;
+        if (idx >= total_px) idx = total_px - 1;
+        if (item + nwarps < count) idx_next = p.q_items[item + nwarps];
         const unsigned per_frame = (unsigned)p.out_rows * (unsigned)p.width;
         const int frame = (int)(idx / per_frame);
         const unsigned rem = idx - (unsigned)frame * per_frame;
@@ -825,30 +845,38 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
         const int y = oy + p.y_off;
         const uint32_t* gsrc = p.guide4 + (long long)frame * p.guide_frame_stride;
         const float* dsrc = p.depth + (long long)frame * p.depth_frame_stride;
-        const uint32_t gpix = __ldg(gsrc + (long long)y * p.guide_pitch + x);
+        // all of the lane's loads are issued before the first use (the taps are independent: one round trip
+        // to L2 per pixel instead of two per tap); out-of-window taps read the centre and are masked
+        float dfl[KMAX];
+        uint32_t gql[KMAX];
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u) {
+            const int ty = y + tdy[u], tx = x + tdx[u];
+            const bool in = tx >= 0 && tx < p.width && ty >= 0 && ty < p.height;
+            const int cy_ = in ? ty : y, cx_ = in ? tx : x;
+            const float df = plain ? __ldg(dsrc + (long long)cy_ * p.width + cx_) : jbf_sample_depth(p, frame, cx_, cy_);
+            gql[u] = __ldg(gsrc + (long long)cy_ * p.guide_pitch + cx_);
+            dfl[u] = in ? df : 0.f;
+        }
+        uint32_t gpix = 0u;
+#pragma unroll
+        for (int u = 0; u < KMAX; ++u)
+            if (u == tc / 32) gpix = __shfl_sync(0xffffffffu, gql[u], tc & 31);
         // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight
         double dl[KMAX], fl[KMAX];
         double a = 0.0, wt = 0.0;
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
-            const int ty = y + tdy[u], tx = x + tdx[u];
-            dl[u] = 0.0;
-            fl[u] = 0.0;
-            if (tx >= 0 && tx < p.width && ty >= 0 && ty < p.height) {
-                const float df = plain ? __ldg(dsrc + (long long)ty * p.width + tx) : jbf_sample_depth(p, frame, tx, ty);
-                if (df > kValidDepth) {
-                    const uint32_t ad = __vabsdiffu4(gpix, __ldg(gsrc + (long long)ty * p.guide_pitch + tx));
-                    const double cd = (double)__dp4a(ad, ad, 0u);
-                    const double f = tsw[u] * exp_neg_f64(cd * p.kc);
-                    dl[u] = (double)df;
-                    fl[u] = f;
-                    a += dl[u] * f;
-                    wt += f;
-                }
-            }
+            const bool v = dfl[u] > kValidDepth;
+            const uint32_t ad = __vabsdiffu4(gpix, gql[u]);
+            const double cd = (double)__dp4a(ad, ad, 0u);
+            const double f = v ? tsw[u] * exp_neg_f64(cd * p.kc) : 0.0;
+            dl[u] = v ? (double)dfl[u] : 0.0;
+            fl[u] = f;
+            a += dl[u] * f;
+            wt += f;
         }
-        a = warp_sum_f64(a);
-        wt = warp_sum_f64(wt);
+        warp_sum2_f64(a, wt);
         float r = 0.f;
         if (wt > 0.0) {
             const double m = a / wt;
@@ -862,8 +890,7 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
                 num += dl[u] * f;
                 den += f;
             }
-            num = warp_sum_f64(num);
-            den = warp_sum_f64(den);
+            warp_sum2_f64(num, den);
             r = (den == 0.0) ? 0.f : (float)(num / den);
         }
         if (lane == 0) {

@@ -140,7 +140,7 @@ struct jbf_handle {
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
-    bool force_no_tma = false, force_big_tiles = false, no_refine = false, no_split_tiles = false;
+    bool force_no_tma = false, force_big_tiles = false, no_refine = false, no_split_tiles = false, no_pdl = false;
     int force_tile_h = 0;
     int last_variant = 0;
     // TMA descriptors of the last fast launch, reused while (pointers, rows, frames, box) are unchanged
@@ -275,6 +275,7 @@ static int build_tables(jbf_handle* h) {
     h->force_big_tiles = getenv("KDME_BIG_TILES") != nullptr;
     h->no_refine = getenv("KDME_NO_REFINE") != nullptr;
     h->no_split_tiles = getenv("KDME_NO_SPLIT_TILES") != nullptr;
+    h->no_pdl = getenv("KDME_NO_PDL") != nullptr;
     if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
     h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
     h->kd = h->use_depth ? 1.0 / (2.0 * (double)h->sigma_d * (double)h->sigma_d) : 0.0;
@@ -403,9 +404,17 @@ static int launch_presmooth(jbf_handle* h, const uint8_t* bgr, size_t bgr_step, 
         p.ksize = h->ps_ksize; p.space_lut = h->ps_space_dev; p.color_lut = h->ps_color_dev;
         p.bgr_up = bgr_up; p.bgr_dn = bgr_dn; p.band0 = band0; p.band1 = band1;
         if (h->ps_ksize == 5) {
-            constexpr int TW = 64, TH = 16;
-            dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
-            presmooth5_kernel<TW, TH><<<grd, (TW / 4) * (TH / 2), 0, h->stream>>>(p);
+            // 64x16 tiles, 128 threads, 4x2 pixels per thread; a launch too small to fill the GPU with them (one
+            // Kinect frame is 300) uses 64x8 tiles of 128 threads with 4x1 pixels: four times the warps
+            constexpr int TW = 64;
+            const long long ctas16 = (long long)((h->width + TW - 1) / TW) * ((rows + 15) / 16) * n;
+            if (ctas16 >= 148LL * 6) {
+                dim3 grd((h->width + TW - 1) / TW, (rows + 15) / 16, n);
+                presmooth5_kernel<TW, 16, 2><<<grd, (TW / 4) * 8, 0, h->stream>>>(p);
+            } else {
+                dim3 grd((h->width + TW - 1) / TW, (rows + 7) / 8, n);
+                presmooth5_kernel<TW, 8, 1><<<grd, (TW / 4) * 8, 0, h->stream>>>(p);
+            }
         } else {
             constexpr int TW = 32, TH = 8;
             dim3 grd((h->width + TW - 1) / TW, (rows + TH - 1) / TH, n);
@@ -473,7 +482,7 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = (pdl && !h->no_pdl) ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, h->map_depth, h->map_guide, p));
     return KDME_OK;
 }
@@ -579,7 +588,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
-                cfg.numAttrs = pdl ? 1 : 0;
+                cfg.numAttrs = (pdl && !h->no_pdl) ? 1 : 0;
                 CK(cudaLaunchKernelEx(&cfg, jbf_upsample_gather_kernel<TW, TH>, p, g));
                 h->last_variant = 0x1000 | 0x400;
                 rc = KDME_OK;
@@ -608,7 +617,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = h->no_pdl ? 0 : 1;
             if (h->radius <= 7) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<8>, p, h->radius));
             else if (h->radius <= 10) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<16>, p, h->radius));
             else CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<31>, p, h->radius));

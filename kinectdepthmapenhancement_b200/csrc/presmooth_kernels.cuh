@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
 // staged pixel is converted ONCE to float b, g, r and a packed u8x4 word, kept as four shared-memory
 // planes so a thread fetches its 8-column row segment with conflict-free 16-byte LDS; a tap is then
 // VABSDIFF4 + IDP.4A (L1 norm) + LDS (colour LUT) + FMUL + 3 FFMA + FADD.
-template <int TW, int TH>
-__global__ void __launch_bounds__((TW / 4) * (TH / 2)) presmooth5_kernel(const PresmoothParams p) {
+template <int TW, int TH, int PY>
+__global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const PresmoothParams p) {
     grid_launch_dependents();   // PDL: the filter's prologue (LUTs, descriptors, barrier) may start now
-    static_assert(TH % 2 == 0, "a thread owns two rows");
-    constexpr int NT = (TW / 4) * (TH / 2), R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
+    static_assert(TH % PY == 0 && (PY == 1 || PY == 2), "a thread owns PY rows");
+    constexpr int NT = (TW / 4) * (TH / PY), R = 2, SP = TW + 8, SH = TH + 2 * R;   // 4 halo columns each side (16-byte rows)
     constexpr int XO = 4 - R;                                               // first used column of a staged row
     __shared__ __align__(16) float sB[SP * SH];
     __shared__ __align__(16) float sG[SP * SH];
@@ -154,25 +154,26 @@ __global__ void __launch_bounds__((TW / 4) * (TH / 2)) presmooth5_kernel(const P
     if (tid < 25) sSp[tid] = __ldg(p.space_lut + tid);
     __syncthreads();
 
-    // each thread owns a 4 x 2 block of pixels: a staged row segment is fetched once and serves the taps of
-    // both output rows (6 row fetches per 8 pixels instead of 10 -- the kernel is bound by shared-memory
-    // wavefronts).  Per pixel the taps are still visited dy-major, dx-minor: same sums, same bits.
-    const int lx = tid % (TW / 4), ly = tid / (TW / 4);   // ly indexes PAIRS of rows
-    uint32_t c[2][4];
-    float s0[2][4], s1[2][4], s2[2][4], ws[2][4];
+    // each thread owns a 4 x PY block of pixels.  PY = 2 (large launches): a staged row segment is fetched once
+    // and serves the taps of both output rows (6 row fetches per 8 pixels instead of 10 -- shared-memory
+    // wavefronts bound the kernel); PY = 1 (one frame): twice the warps, half the serial work per thread.
+    // Per pixel the taps are visited dy-major, dx-minor either way: same sums, same bits.
+    const int lx = tid % (TW / 4), ly = tid / (TW / 4);   // ly indexes groups of PY rows
+    uint32_t c[PY][4];
+    float s0[PY][4], s1[PY][4], s2[PY][4], ws[PY][4];
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-        const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (2 * ly + o + R) * SP + 4 * lx + 4);
+    for (int o = 0; o < PY; ++o) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(sP + (PY * ly + o + R) * SP + 4 * lx + 4);
         c[o][0] = c4.x; c[o][1] = c4.y; c[o][2] = c4.z; c[o][3] = c4.w;
 #pragma unroll
         for (int k = 0; k < 4; ++k) { s0[o][k] = 0.f; s1[o][k] = 0.f; s2[o][k] = 0.f; ws[o][k] = 0.f; }
     }
 #pragma unroll
-    for (int sr = 0; sr < 6; ++sr) {
+    for (int sr = 0; sr < 4 + PY; ++sr) {
         // columns [4*lx, 4*lx + 12) of the staged row: pixel k, tap dx sits at local column XO + k + dx
         float rb[12], rg[12], rr[12];
         uint32_t rp[12];
-        const int base = (2 * ly + sr) * SP + 4 * lx;
+        const int base = (PY * ly + sr) * SP + 4 * lx;
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             const float4 b4 = *reinterpret_cast<const float4*>(sB + base + 4 * v);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__((TW / 4) * (TH / 2)) presmooth5_kernel(const P
             rp[4 * v] = p4.x; rp[4 * v + 1] = p4.y; rp[4 * v + 2] = p4.z; rp[4 * v + 3] = p4.w;
         }
 #pragma unroll
-        for (int o = 0; o < 2; ++o) {
+        for (int o = 0; o < PY; ++o) {
             const int dy = sr - o;
             if (dy < 0 || dy > 4) continue;   // compile time
 #pragma unroll
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__((TW / 4) * (TH / 2)) presmooth5_kernel(const P
     const int gx = x0 + 4 * lx;
     if (gx >= p.width) return;
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-        const int gy = y0 + 2 * ly + o;
+    for (int o = 0; o < PY; ++o) {
+        const int gy = y0 + PY * ly + o;
         if (gy >= p.height) continue;
         uint32_t ov[4];
 #pragma unroll

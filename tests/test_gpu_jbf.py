@@ -499,3 +499,28 @@ def test_filter_guide4_rejects_mismatched_tensors():
         f.filter_guide4(d, g, out=d)
     with pytest.raises(ValueError):
         f.filter_guide4(torch.zeros((2, 48, 32), device="cuda"), g)
+
+
+@pytest.mark.parametrize("wl,hl,wh,hh,r", [(512, 424, 1920, 1080, 7), (64, 48, 64, 48, 3), (50, 37, 131, 97, 5),
+                                         (100, 80, 127, 90, 2), (17, 9, 640, 480, 15), (33, 20, 70, 50, 7)])
+def test_upsample_gather_equals_dense_bit_for_bit(wl, hl, wh, hh, r):
+    """The gather form (site lattice only) and the dense kernel on the scattered tile are the same arithmetic:
+    every scale from 1:1 to 37:1, ragged sizes, radii 2..15, holes in the low-res map."""
+    from kinectdepthmapenhancement_b200 import synth
+    lo, _ = synth.rgbd_frame(wl, hl, seed=6, frame=r, noise_rel=0.01, device="cuda", hole_frac=0.1)
+    _, hi = synth.rgbd_frame(wh, hh, seed=6, frame=r, device="cuda")
+    f = _jbf_cls()(wh, hh, window_radius=r)
+    a = f.Upsampling(lo, hi).clone()
+    va = f.kernel_variant
+    os.environ["KDME_UPSAMPLE_DENSE"] = "1"
+    try:
+        b = f.Upsampling(lo, hi).clone()
+    finally:
+        os.environ.pop("KDME_UPSAMPLE_DENSE", None)
+    vb = f.kernel_variant
+    assert (va & 0x1000) and not (vb & 0x1000)
+    assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    sparse = oracle.scatter_lowres(lo.cpu().numpy(), wh, hh)
+    if wh * hh <= 200 * 200:
+        guide = oracle.presmooth(hi.cpu().numpy())
+        check_against_f64(a.cpu().numpy(), sparse, guide, 2 * r + 1, 70.0, 50.0, 20.0, f"upsample {wl}x{hl}->{wh}x{hh}")
