@@ -99,9 +99,9 @@ int jbf_presmooth(jbf_handle *h, const uint8_t *bgr_dev, size_t bgr_step, uint8_
 /* Row-band forms (one very large frame split into row bands across GPUs).  The
  * arrays hold `rows` rows = the band plus whatever halo rows exist on each side (image borders
  * have none); jbf_filter_rows writes only rows [y_off, y_off + out_rows) into out_dev (out_rows
- * rows).  Tiles start at y_off, so a band starting on a multiple of 16 image rows is tiled exactly
- * like the whole image and the result equals the single-GPU result bit for bit.  `rows` comes
- * from the arguments (the handle's height is not used by these two calls). */
+ * rows).  A pixel's arithmetic depends only on the image around it, never on the tile or band it
+ * falls in, so any band split equals the single-GPU result bit for bit (whatever tile height either
+ * launch picks).  `rows` comes from the arguments (the handle's height is not used by these calls). */
 int jbf_presmooth_rows(jbf_handle *h, const uint8_t *bgr_dev, size_t bgr_step, uint8_t *guide4_dev,
                        size_t guide_step, int rows);
 int jbf_filter_rows(jbf_handle *h, const float *depth_dev, const uint8_t *guide4_dev, size_t guide_step,

@@ -11,7 +11,8 @@ needs to use 2/4/8 B200s, one process per GPU over torch.distributed:
   locally on the halo and ONE neighbour exchange per frame suffices: a batched isend/irecv
   (ncclSend/ncclRecv inside one group over NVLink with the NCCL backend).  Edge ranks skip the
   missing neighbour; the image border is the kernel's zero fill.  The band result equals the
-  single-GPU result bit for bit (same tiles, same summation order).
+  single-GPU result bit for bit: a pixel's arithmetic depends only on the image around it, not on the
+  tile or band it falls in (band boundaries are kept on multiples of 16 rows only for even tiling).
 
 Everything in HaloExchanger works on CPU tensors with the gloo backend too (used by the CPU tests).
 """
@@ -226,8 +227,8 @@ class RowBandJBF:
     def process(self, exchange: bool = True, overlap: bool = True) -> torch.Tensor:
         """Filter this rank's band.  With overlap=True the neighbour exchange runs while the band's interior
         rows (those whose window and pre-smooth footprint stay inside the band) are filtered; the two seam
-        strips follow once the halos have landed.  Strips start on tile rows, so the result is bit-identical
-        to the unsplit launch and to the single-GPU frame."""
+        strips follow once the halos have landed.  The result is bit-identical to the unsplit launch and to the
+        single-GPU frame (tile-independent arithmetic)."""
         p = self.plan
         if self.peer_memory:
             return self.process_peer(barrier=exchange)
