@@ -141,7 +141,7 @@ struct jbf_handle {
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
     int cd_skip = INT_MAX, use_color = 1, use_depth = 1;
     bool force_no_tma = false, force_big_tiles = false, no_refine = false, no_split_tiles = false, no_pdl = false;
-    int force_tile_h = 0;
+    int force_tile_h = 0, res_limit = 0;
     int last_variant = 0;
     // TMA descriptors of the last fast launch, reused while (pointers, rows, frames, box) are unchanged
     struct MapKey { const void* depth = nullptr; const void* guide = nullptr; int rows = 0, n = 0, gp = 0, bx = 0, by = 0; } map_key;
@@ -277,6 +277,7 @@ static int build_tables(jbf_handle* h) {
     h->no_split_tiles = getenv("KDME_NO_SPLIT_TILES") != nullptr;
     h->no_pdl = getenv("KDME_NO_PDL") != nullptr;
     if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
+    if (const char* rl = getenv("KDME_RES_LIMIT")) h->res_limit = atoi(rl);
     h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
     h->kd = h->use_depth ? 1.0 / (2.0 * (double)h->sigma_d * (double)h->sigma_d) : 0.0;
     // refine in fp64 when the mean range weight den/wsum (biases removed) is below 2^-8
@@ -432,14 +433,17 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, b
     using T = JbfTile<R, TW, TH>;
     // resident CTAs per SM: by registers (<= 80 for r <= 9, <= 128 above: the row segment alone is
     // 3 x (2r + 8) registers) and by shared memory
-    constexpr int kByRegs = (R <= 9 ? 65536 / 80 : 65536 / 128) / T::NT;
+    // registers: r <= 5 runs best at 80, r = 6..9 at 64 (one more resident CTA of 256 threads, +2.5 % measured),
+    // larger windows need 128 (the row segment alone is 3 x (2r + 8) registers)
+    constexpr int kByRegs = (R <= 5 ? 65536 / 80 : R <= 9 ? 65536 / 64 : 65536 / 128) / T::NT;
     constexpr int kBySmem = (227 * 1024) / (T::SMEM + 1024);
     constexpr int MINB = (kByRegs < kBySmem ? kByRegs : kBySmem) < 1 ? 1 : (kByRegs < kBySmem ? kByRegs : kBySmem);
     auto kern = jbf_fast_kernel<R, TW, TH, MINB>;
     static std::atomic<unsigned long long> attr_done{0};   // one bit per device
     const unsigned long long bit = 1ull << (h->device & 63);
+    constexpr int kSmemCap = 226 * 1024;
     if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));
         attr_done.fetch_or(bit, std::memory_order_release);
     }
     if (want_tma) {
@@ -473,10 +477,24 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, b
         const int rem = p.out_rows - nbig * TH;
         if (nbig >= 1 && rem > 0) { p.nbig_rows = nbig; tile_rows = nbig + (rem + p.ts - 1) / p.ts; }
     }
+    // A launch of less than one full wave: the block scheduler packs CTAs onto SMs up to the residency limit
+    // and leaves the other SMs idle, so the limit is lowered to what the launch needs (ceil(CTAs / 148)) by
+    // padding the dynamic shared memory request -- every SM then gets its share.
+    size_t smem_bytes = T::SMEM;
+    {
+        const long long grid_ctas = (long long)tx * tile_rows * p.n_frames;
+        int want_res = (int)((grid_ctas + 147) / 148);
+        if (h->res_limit > 0) want_res = h->res_limit;
+        if (want_res < 1) want_res = 1;
+        if (want_res < MINB) {
+            const size_t padded = (size_t)(228 * 1024) / (size_t)want_res - 1024 - 512;   // 1 KB per CTA is reserved by the system
+            if (padded > smem_bytes) smem_bytes = padded > (size_t)kSmemCap ? (size_t)kSmemCap : padded;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tx, tile_rows, p.n_frames);
     cfg.blockDim = dim3(T::NT);
-    cfg.dynamicSmemBytes = T::SMEM;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
