@@ -544,13 +544,19 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
     uint32_t* sSg = reinterpret_cast<uint32_t*>(sSd + g.nrow_max * g.ncol_max);   // guide word at the site
     int* sXs = reinterpret_cast<int*>(sSg + g.nrow_max * g.ncol_max);    // [ncol_max] site x
     int* sYs = sXs + g.ncol_max;                                         // [nrow_max] site y
-    float* sL1 = reinterpret_cast<float*>(sYs + g.nrow_max);             // [WS][WS]
-    float* sL2 = sL1 + WS * WS;
+    float* sL1 = reinterpret_cast<float*>(sYs + g.nrow_max + ((g.ncol_max + g.nrow_max) & 1));   // [WS][WS+1] pairs {L[jj], L[jj-1]} (8-byte aligned)
+    float* sL2 = sL1 + WS * (WS + 1) * 2;
     __shared__ int sN[2];
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    for (int idx = tid; idx < WS * WS; idx += NT) { sL1[idx] = __ldg(g.ltab1 + idx); sL2[idx] = __ldg(g.ltab2 + idx); }
+    for (int idx = tid; idx < WS * (WS + 1); idx += NT) {   // padded pair tables from the plain [WS][WS] ones
+        const int i = idx / (WS + 1), jj = idx - i * (WS + 1);
+        const float a1 = (jj < WS) ? __ldg(g.ltab1 + i * WS + jj) : 0.f, b1 = (jj > 0) ? __ldg(g.ltab1 + i * WS + jj - 1) : 0.f;
+        const float a2 = (jj < WS) ? __ldg(g.ltab2 + i * WS + jj) : 0.f, b2 = (jj > 0) ? __ldg(g.ltab2 + i * WS + jj - 1) : 0.f;
+        sL1[2 * idx] = a1; sL1[2 * idx + 1] = b1;
+        sL2[2 * idx] = a2; sL2[2 * idx + 1] = b2;
+    }
     grid_dependency_wait();
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.q_count_prev = 0u;
     // site columns with x in [x0 - R, x0 + TW - 1 + R], site rows with y in [y0 - R, y0 + TH - 1 + R]
@@ -624,77 +630,101 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
     const float ncO = -cO;
     const float nkc = p.nkc;
 
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f}, accl[4] = {0.f, 0.f, 0.f, 0.f}, wsl[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int sr = r_lo; sr < r_hi; ++sr) {
-        const int i = sYs[sr] - gy + R;
-        float racc[4] = {0.f, 0.f, 0.f, 0.f}, rws[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int sc = c_lo; sc < c_hi; ++sc) {
-            const float d = sSd[sr * g.ncol_max + sc];
-            if (d == 0.f) continue;
-            const uint32_t gq = sSg[sr * g.ncol_max + sc];
-            const float dsh = fmaf(d, sq, ncO);
-            const int jb = sXs[sc] - gx + R;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = jb - k;
-                if (j >= 0 && j < WS) {
-                    const uint32_t ad = __vabsdiffu4(gp[k], gq);
-                    const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;   // exact integer, no I2F
-                    const float f = ex2_approx(fmaf(cdf, nkc, sL1[i * WS + j]));
-                    racc[k] = fmaf(f, dsh, racc[k]);
-                    rws[k] += f;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {   // Knuth 2Sum, as two_sum2 does per lane
-            float s_ = acc[k] + racc[k], bb = s_ - acc[k];
-            accl[k] += (acc[k] - (s_ - bb)) + (racc[k] - bb);
-            acc[k] = s_;
-            s_ = wsum[k] + rws[k]; bb = s_ - wsum[k];
-            wsl[k] += (wsum[k] - (s_ - bb)) + (rws[k] - bb);
-            wsum[k] = s_;
-        }
-    }
-    float delta[4];
+    // Branch-free taps in the dense kernel's packed form: pixels (0,1) and (2,3) share a site, lane 0 of a pair
+    // sees it at window column j0 and lane 1 at j0 - 1; a lane whose column falls outside the window (or a site
+    // that is a hole) gets weight exactly 0, which adds nothing -- the sums are the dense kernel's, bit for bit.
+    const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+    const f32x2 nkc2 = pack2(nkc, nkc);
+    const int LPW = WS + 1;   // padded pair-table row: entry jj = {L[jj], L[jj-1]}, jj = 0..WS
+    float wsum[4], delta[4];
     bool any[4];
+    {
+        f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull}, accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};
+        for (int sr = r_lo; sr < r_hi; ++sr) {
+            const float2* lrow = reinterpret_cast<const float2*>(sL1) + (sYs[sr] - gy + R) * LPW;
+            f32x2 raccP[2] = {0ull, 0ull}, rwsP[2] = {0ull, 0ull};
+            for (int sc = c_lo; sc < c_hi; ++sc) {
+                const float d = sSd[sr * g.ncol_max + sc];
+                const bool valid = d != 0.f;
+                const uint32_t gq = sSg[sr * g.ncol_max + sc];
+                const float dsh = fmaf(d, sq, ncO);
+                const f32x2 dsh2 = pack2(dsh, dsh);
+                const int jb = sXs[sc] - gx + R;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        any[k] = wsum[k] > 0.f;
-        const float dh = acc[k] / wsum[k];
-        float res = fmaf(-dh, wsum[k], acc[k]);
-        res += accl[k];
-        res = fmaf(-dh, wsl[k], res);
-        delta[k] = any[k] ? (dh + res / wsum[k]) : 0.f;
-    }
-    const float e_thr = p.e_thr;
-    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int sr = r_lo; sr < r_hi; ++sr) {
-        const int i = sYs[sr] - gy + R;
-        float rnum[4] = {0.f, 0.f, 0.f, 0.f}, rden[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int sc = c_lo; sc < c_hi; ++sc) {
-            const float d = sSd[sr * g.ncol_max + sc];
-            if (d == 0.f) continue;
-            const uint32_t gq = sSg[sr * g.ncol_max + sc];
-            const float dsh = fmaf(d, sq, ncO);
-            const int jb = sXs[sc] - gx + R;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = jb - k;
-                if (j >= 0 && j < WS) {
-                    const uint32_t ad = __vabsdiffu4(gp[k], gq);
-                    const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;   // exact integer, no I2F
-                    float arg = fmaf(cdf, nkc, sL2[i * WS + j]);
-                    const float e = dsh - delta[k];
-                    if (!(fabsf(e) > e_thr)) arg = fmaf(-e, e, arg);
-                    const float f = ex2_approx(arg);
-                    rnum[k] = fmaf(f, e, rnum[k]);
-                    rden[k] += f;
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int j0 = jb - 2 * pr;
+                    const bool m0 = valid & ((unsigned)j0 < (unsigned)WS), m1 = valid & ((unsigned)(j0 - 1) < (unsigned)WS);
+                    const float2 lp = lrow[min(max(j0, 0), WS)];
+                    const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
+                    const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, kMagicValid)), __uint_as_float(__dp4a(ad1, ad1, kMagicValid)));
+                    const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(lp.x, lp.y));
+                    float a0, a1;
+                    unpack2(ar, a0, a1);
+                    const f32x2 ff = pack2(m0 ? ex2_approx(a0) : 0.f, m1 ? ex2_approx(a1) : 0.f);
+                    raccP[pr] = fma2(ff, dsh2, raccP[pr]);
+                    rwsP[pr] = add2(rwsP[pr], ff);
                 }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { num[k] += rnum[k]; den[k] += rden[k]; }
+            for (int pr = 0; pr < 2; ++pr) {
+                two_sum2(accP[pr], raccP[pr], accL[pr]);
+                two_sum2(wsP[pr], rwsP[pr], wsL[pr]);
+            }
+        }
+        float acc[4], accl[4], wsl[4];
+        unpack2(accP[0], acc[0], acc[1]); unpack2(accP[1], acc[2], acc[3]);
+        unpack2(wsP[0], wsum[0], wsum[1]); unpack2(wsP[1], wsum[2], wsum[3]);
+        unpack2(accL[0], accl[0], accl[1]); unpack2(accL[1], accl[2], accl[3]);
+        unpack2(wsL[0], wsl[0], wsl[1]); unpack2(wsL[1], wsl[2], wsl[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            any[k] = wsum[k] > 0.f;
+            const float dh = acc[k] / wsum[k];
+            float res = fmaf(-dh, wsum[k], acc[k]);
+            res += accl[k];
+            res = fmaf(-dh, wsl[k], res);
+            delta[k] = any[k] ? (dh + res / wsum[k]) : 0.f;
+        }
+    }
+    float num[4], den[4];
+    {
+        const f32x2 ndelP[2] = {pack2(-delta[0], -delta[1]), pack2(-delta[2], -delta[3])};
+        const float e_thr = p.e_thr;
+        f32x2 numP[2] = {0ull, 0ull}, denP[2] = {0ull, 0ull};
+        for (int sr = r_lo; sr < r_hi; ++sr) {
+            const float2* lrow = reinterpret_cast<const float2*>(sL2) + (sYs[sr] - gy + R) * LPW;
+            f32x2 rnumP[2] = {0ull, 0ull}, rdenP[2] = {0ull, 0ull};
+            for (int sc = c_lo; sc < c_hi; ++sc) {
+                const float d = sSd[sr * g.ncol_max + sc];
+                const bool valid = d != 0.f;
+                const uint32_t gq = sSg[sr * g.ncol_max + sc];
+                const float dsh = fmaf(d, sq, ncO);
+                const f32x2 dsh2 = pack2(dsh, dsh);
+                const int jb = sXs[sc] - gx + R;
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    const int j0 = jb - 2 * pr;
+                    const bool m0 = valid & ((unsigned)j0 < (unsigned)WS), m1 = valid & ((unsigned)(j0 - 1) < (unsigned)WS);
+                    const float2 lp = lrow[min(max(j0, 0), WS)];
+                    const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
+                    const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, kMagicValid)), __uint_as_float(__dp4a(ad1, ad1, kMagicValid)));
+                    const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(lp.x, lp.y));
+                    const f32x2 ee = add2(dsh2, ndelP[pr]);
+                    float a0, a1, e0, e1;
+                    unpack2(ar, a0, a1);
+                    unpack2(ee, e0, e1);
+                    if (!(fabsf(e0) > e_thr)) a0 = fmaf(-e0, e0, a0);
+                    if (!(fabsf(e1) > e_thr)) a1 = fmaf(-e1, e1, a1);
+                    const f32x2 ff = pack2(m0 ? ex2_approx(a0) : 0.f, m1 ? ex2_approx(a1) : 0.f);
+                    rnumP[pr] = fma2(ff, ee, rnumP[pr]);
+                    rdenP[pr] = add2(rdenP[pr], ff);
+                }
+            }
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) { numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
+        }
+        unpack2(numP[0], num[0], num[1]); unpack2(numP[1], num[2], num[3]);
+        unpack2(denP[0], den[0], den[1]); unpack2(denP[1], den[2], den[3]);
     }
 
     float o[4];

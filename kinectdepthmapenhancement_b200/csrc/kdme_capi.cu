@@ -588,8 +588,8 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
             g.ltab1 = h->ltab_generic1_dev;
             g.ltab2 = h->ltab_generic_dev;
             const int ws_ = 2 * h->radius + 1;
-            const size_t smem = (size_t)g.ncol_max * g.nrow_max * 8 + (size_t)(g.ncol_max + g.nrow_max) * 4 +
-                                (size_t)ws_ * ws_ * 8 + 16;
+            const size_t smem = (size_t)g.ncol_max * g.nrow_max * 8 + (size_t)(g.ncol_max + g.nrow_max + 1) * 4 +
+                                (size_t)ws_ * (ws_ + 1) * 16 + 16;
             if (smem <= 200 * 1024) {
                 static std::atomic<unsigned long long> attr_done{0};
                 const unsigned long long bit = 1ull << (h->device & 63);
