@@ -1,4 +1,6 @@
 #!/bin/bash
+# N-GPU session (gpurun --gpus N -- bash tools/gpu_session_multi.sh N): the real multi-rank band test, the bare host copy ceiling and the full
+# bench line at N ranks.
 # N-GPU session: real multi-rank band test, copy ceiling, full bench
 N=${1:-2}
 mkdir -p gpurun_out

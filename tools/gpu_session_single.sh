@@ -1,4 +1,6 @@
 #!/bin/bash
+# One-GPU evidence session (gpurun -- bash tools/gpu_session_single.sh): parity tests, smoke, the full bench line, then ONE ncu --set full
+# capture of the dominant kernel after the same command ran clean.  Outputs land in gpurun_out/; copy what is cited into profiles/.
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-300
