@@ -816,18 +816,18 @@ __device__ __forceinline__ double exp_neg_f64(double x) {
     const double tn = t + kMagic;
     const int n = __double2loint(tn);
     const double f = (t - (tn - kMagic)) * 0.6931471805599453; // natural-log units, |f| <= 0.3466
-    double p = 2.505210838544172e-08;                          // 1/11!
-    p = fma(p, f, 2.755731922398589e-07);
-    p = fma(p, f, 2.755731922398589e-06);
-    p = fma(p, f, 2.48015873015873e-05);
-    p = fma(p, f, 1.984126984126984e-04);
-    p = fma(p, f, 1.388888888888889e-03);
-    p = fma(p, f, 8.333333333333333e-03);
-    p = fma(p, f, 4.166666666666666e-02);
-    p = fma(p, f, 1.666666666666667e-01);
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
+    // Estrin evaluation of sum_{k=0..11} f^k / k! (dependency depth 5 instead of 11: the refinement kernel is
+    // latency-bound on its fp64 chains)
+    const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
+    const double q0 = fma(f, 1.0, 1.0);                                            // 1/0! + f/1!
+    const double q1 = fma(f, 1.666666666666667e-01, 0.5);                          // 1/2! + f/3!
+    const double q2 = fma(f, 8.333333333333333e-03, 4.166666666666666e-02);        // 1/4! + f/5!
+    const double q3 = fma(f, 1.984126984126984e-04, 1.388888888888889e-03);        // 1/6! + f/7!
+    const double q4 = fma(f, 2.755731922398589e-06, 2.48015873015873e-05);         // 1/8! + f/9!
+    const double q5 = fma(f, 2.505210838544172e-08, 2.755731922398589e-07);        // 1/10! + f/11!
+    const double r0 = fma(q1, f2, q0), r1 = fma(q3, f2, q2), r2 = fma(q5, f2, q4);
+    double p = fma(r1, f4, r0);
+    p = fma(r2, f8, p);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
@@ -863,7 +863,6 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
     const unsigned pushed = *reinterpret_cast<volatile unsigned int*>(p.q_count);
     const unsigned count = pushed < p.q_capacity ? pushed : p.q_capacity;
     const bool plain = (p.mode != kStageUpsample) && p.depth_up == nullptr && p.depth_dn == nullptr;
-    const int tc = radius * ws + radius;   // the centre tap: lane tc % 32 holds the centre's guide word in slot tc / 32
     for (unsigned item = first; item < count; item += nwarps) {
         unsigned idx = idx_next;
         if (idx >= total_px) idx = total_px - 1;
@@ -879,6 +878,7 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
         // to L2 per pixel instead of two per tap); out-of-window taps read the centre and are masked
         float dfl[KMAX];
         uint32_t gql[KMAX];
+        const uint32_t gpix = __ldg(gsrc + (long long)y * p.guide_pitch + x);   // same batch of loads as the taps
 #pragma unroll
         for (int u = 0; u < KMAX; ++u) {
             const int ty = y + tdy[u], tx = x + tdx[u];
@@ -888,10 +888,6 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
             gql[u] = __ldg(gsrc + (long long)cy_ * p.guide_pitch + cx_);
             dfl[u] = in ? df : 0.f;
         }
-        uint32_t gpix = 0u;
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u)
-            if (u == tc / 32) gpix = __shfl_sync(0xffffffffu, gql[u], tc & 31);
         // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight
         double dl[KMAX], fl[KMAX];
         double a = 0.0, wt = 0.0;
