@@ -254,11 +254,12 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_fast_kernel(const __grid_
             const bool pr = (d != 0.f) & (sLab[q] == lp);
             const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
             const float cdf = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;
-            float f = ex2_approx(fmaf(cdf, nk0, p.ltab[i * WS + j]));
-            f = pr ? f : 0.f;
-            acc = fmaf(f, d - d0, acc);
-            wsum += f;
-            same |= pr ? (1ull << (i * WS + j)) : 0ull;
+            const float f = ex2_approx(fmaf(cdf, nk0, p.ltab[i * WS + j]));
+            if (pr) {   // predicated accumulation (no selects)
+                acc = fmaf(f, d - d0, acc);
+                wsum += f;
+                same |= 1ull << (i * WS + j);
+            }
         }
     float o = 0.f;
     if (wsum > 0.f) {
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_fast_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < WS; ++j) {
                 const float x = fabsf((sD[base + i * SP + j] - d0) - delta);
-                dev += ((same >> (i * WS + j)) & 1ull) ? x : 0.f;
+                if ((same >> (i * WS + j)) & 1ull) dev += x;
             }
         const int count = __popcll(same);
         if (count != 0) dev /= (float)count;
@@ -284,7 +285,6 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_fast_kernel(const __grid_
         const float e_thr = (float)1.2247448713915890e1;  // sqrt(150)
         float sigma = p.sigma_c;
         float num = 0.f, den = 0.f;
-        bool poisoned = false;
 #pragma unroll
         for (int i = 0; i < WS; ++i)
 #pragma unroll
@@ -295,30 +295,46 @@ __global__ void __launch_bounds__(TW * TH) guided_fill_fast_kernel(const __grid_
                 const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
                 const float cd = __uint_as_float(__dp4a(ad, ad, kMagicValid)) - 8388608.0f;
                 float lg = p.ltab[i * WS + j];
-                // the recurrence advances once per VALID tap while sigma != 0 (:170-176)
+                // the recurrence advances once per VALID tap while sigma != 0 (:170-176); branch-free
                 const bool adv = v & (sigma != 0.0f);
                 const float t = sigma * 0.3f;
                 const float sn = (adaptive > t) ? adaptive : t;
                 sigma = adv ? sn : sigma;
-                const float dn = 2 * (sigma * sigma);
-                if (dn > 1.0e-30f) {
-                    float rc;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dn));
-                    const float a = -cd * rc;
-                    if (adv & (a >= kZero)) lg = fmaf(a, l2e, lg);
-                } else if (adv & (cd == 0.f)) {
-                    // cd >= 1 over a denominator <= 1e-30 is beyond the fp32 expf() cut-off: factor skipped.
-                    // cd == 0: -0/dn = -0 (factor 1) unless sigma^2 underflowed to 0: -0/0 = NaN poisons the pixel
-                    if (dn == 0.f) poisoned = true;
-                }
+                // a = -cd / (2 sigma^2) evaluated as (-cd * rcp(sigma^2)) with the factor 1/2 folded into the constants
+                // (a power of two: same bits)
+                const float s2 = sigma * sigma;
+                float rc;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(s2));
+                const float a2 = -cd * rc;                      // 2a
+                // 2 sigma^2 <= 1e-30: cd >= 1 is beyond the fp32 expf() cut-off (factor skipped) and cd == 0 gives -0
+                // (factor 1) -- either way nothing is added; the one exception, -0/0 = NaN, is handled after the sweep
+                if (adv & (s2 > 0.5e-30f) & (a2 >= 2.0f * kZero)) lg = fmaf(a2, 0.5f * l2e, lg);
                 const float e = (d - d0) - delta;
                 const float es = e * sq;
                 if (!(fabsf(es) > e_thr)) lg = fmaf(-es, es, lg);
-                float f = ex2_approx(lg);
-                f = v ? f : 0.f;
-                num = fmaf(f, e, num);
-                den += f;
+                const float f = ex2_approx(lg);
+                if (v) {
+                    num = fmaf(f, e, num);
+                    den += f;
+                }
             }
+        // NaN poisoning (:170-176 with sigma^2 underflowed to exactly 0 and cd == 0: expf(-0/0) = NaN).  sigma never
+        // increases once the sweep has started, so it can only have happened if the FINAL sigma squares to 0: rare,
+        // re-walked here with the recurrence alone
+        bool poisoned = false;
+        if (sigma != 0.0f ? (2 * (sigma * sigma) == 0.0f) : true) {
+            float sg = p.sigma_c;
+            for (int t2 = 0; t2 < WS * WS; ++t2) {
+                const int q = base + (t2 / WS) * SP + (t2 % WS);
+                if (sD[q] == 0.f || sg == 0.0f) continue;
+                const float tt = sg * 0.3f;
+                sg = (adaptive > tt) ? adaptive : tt;
+                if (2 * (sg * sg) == 0.0f) {
+                    const uint32_t ad = __vabsdiffu4(gpix, sG[q]);
+                    if (__dp4a(ad, ad, 0u) == 0u) poisoned = true;
+                }
+            }
+        }
         if (poisoned) o = __int_as_float(0x7fc00000);
         else o = (den == 0.0f) ? 0.0f : mean + num / den;
     }

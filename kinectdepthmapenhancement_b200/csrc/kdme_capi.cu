@@ -773,6 +773,12 @@ extern "C" int jbf_process_xyz(jbf_handle* h, const float* depth_dev, const uint
                                float* xyz_dev, float fx, float fy, int cx, int cy) {
     if (!h || !depth_dev || !bgr_dev || !xyz_dev) return fail(KDME_EINVAL, "jbf_process_xyz: NULL argument");
     if (!(fx != 0.f) || !(fy != 0.f)) return fail(KDME_EINVAL, "jbf_process_xyz: focal lengths must be non-zero");
+    if (!h->fast) {   // exotic sigmas / radius 0 (generic kernel): the two calls the reference makes, back to back
+        int rc2 = jbf_process_batch(h, depth_dev, bgr_dev, bgr_step, h->filtered_dev, 1);
+        if (rc2 != KDME_OK) return rc2;
+        DeviceGuard g(h->device);
+        return kdme_projective_to_real(h->filtered_dev, xyz_dev, h->width, h->height, fx, fy, cx, cy, h->stream);
+    }
     h->xyz_out = xyz_dev; h->xyz_fx = fx; h->xyz_fy = fy; h->xyz_cx = cx; h->xyz_cy = cy; h->xyz_yimg0 = 0;
     const int rc = jbf_process_batch(h, depth_dev, bgr_dev, bgr_step, h->filtered_dev, 1);
     h->xyz_out = nullptr;

@@ -437,9 +437,9 @@ def test_process_xyz_equals_projective_to_real_of_filtered():
     """f3 as SURVEY 8(f) asks: back-projection fused into the filter epilogue (main.cpp:179 + :182 as one launch
     pair) is bit-identical to projectiveToReal(filtered) -- also on the pixels re-evaluated in fp64."""
     from kinectdepthmapenhancement_b200 import projective_to_real, synth
-    for (w, h, r) in [(640, 480, 7), (322, 241, 2), (70, 50, 3)]:
+    for (w, h, r, sc) in [(640, 480, 7, 50.0), (322, 241, 2, 50.0), (70, 50, 3, 50.0), (96, 64, 3, 20.0)]:   # last: generic kernel
         depth, bgr = synth.rgbd_frame(w, h, seed=8, frame=0, device="cuda")
-        f = _jbf_cls()(w, h, window_radius=r)
+        f = _jbf_cls()(w, h, 70.0, sc, 20.0, window_radius=r)
         xyz = f.process_xyz(depth, bgr, 525.0, 520.0, w // 2, h // 2)
         filt = f.getFiltered_Device().clone()
         f.Process(depth, bgr)
