@@ -9,9 +9,8 @@
 //     (cp.async.bulk.tensor, zero fill outside the image == the reference's
 //     bounds test, .cu:21) -- or by plain coalesced loads when the frame pitch
 //     is not 16-byte aligned, or by an on-the-fly low-res scatter (Upsampling);
-//   * a prepare step rewrites the staged depth as (d - d_ref) * sqrt(log2e/2sd^2)
-//     (d_ref = smallest valid depth of the staged tile) and emits one "magic"
-//     word per staged pixel that carries validity (d > 50);
+//   * one sweep emits a "magic" word per staged sample that carries validity
+//     (d > 50; holes and NaN read as depth 0);
 //   * each thread owns 4 horizontally adjacent pixels and sweeps the window row
 //     by row; a staged row segment is fetched once with 16-byte LDS and reused
 //     by all 4 pixels (4*(2r+1) taps per 2r+4 fetched columns);
@@ -20,9 +19,18 @@
 //     + colour term) [+ FADD, FSETP, predicated FFMA for the depth-range term
 //     in pass 2] + ONE MUFU.EX2 + FFMA + FADD.  No expf, no division, no
 //     branch per tap;
-//   * sums are accumulated around local origins (tile d_ref, per-thread d0,
-//     per-pixel pass-1 mean), which is what makes fp32 agree with the fp64
-//     evaluation of the reference formula to ~1 ulp of the output.
+//   * precision: depths enter as X = d*sq - fl(d0*sq) around a per-thread origin d0
+//     (one rounding, relative to the small difference), pass-1 weights carry no
+//     bias, row sums are combined with 2Sum, the mean is the correctly rounded
+//     quotient of the compensated sums: every well-conditioned pixel lands within
+//     1-2 ulps of the fp64 evaluation of the reference formula, independently of
+//     the tile it falls in;
+//   * pixels whose window holds no sample near the pass-1 mean (den/wsum tiny)
+//     amplify the rounding of that mean beyond what fp32 can absorb: they are
+//     queued and re-evaluated in fp64 by jbf_refine_kernel (one warp per pixel,
+//     taps split across lanes, warp-shuffle reductions);
+//   * the epilogue can also write the back-projected float3 cloud
+//     (DimensionConvertor::projectiveToReal fused, main.cpp:179 + :182).
 //
 // The reference's quirks are kept: > 50 validity, hole filling (centre need not
 // be valid), skip-if-zero guards (spatial: folded into the LUT; colour: cannot

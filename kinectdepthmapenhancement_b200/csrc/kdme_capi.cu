@@ -197,7 +197,6 @@ static int build_tables(jbf_handle* h) {
     h->bias1 = (lmin + cmin > -120.0) ? 0.f : kWeightBias;
     const int lpp = (ws - 1 + 1) & ~1;
     std::vector<float> lpairs((size_t)ws * (lpp > 0 ? lpp : 1) * 2, 0.f), lpairs1(lpairs.size(), 0.f);
-    const float dbias = h->bias1 - kWeightBias;
     for (int i = 0; i < ws; i++)
         for (int j = 1; j < ws; j++) {
             lpairs[((size_t)i * lpp + (j - 1)) * 2 + 0] = lf[(size_t)i * lp + j];
@@ -210,7 +209,6 @@ static int build_tables(jbf_handle* h) {
             if (j >= 1) lpairs1[((size_t)i * lpp + (j - 1)) * 2 + 0] = l1;
             if (j + 1 < ws) lpairs1[((size_t)i * lpp + j) * 2 + 1] = l1;
         }
-    (void)dbias;
     CK(cudaMalloc(&h->ltab_pairs_dev, lpairs.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->ltab_pairs_dev, lpairs.data(), lpairs.size() * sizeof(float), cudaMemcpyHostToDevice,
                        h->stream));
