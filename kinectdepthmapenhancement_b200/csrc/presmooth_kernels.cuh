@@ -122,31 +122,42 @@ __global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const 
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, frame = blockIdx.z;
     const uint8_t* src = p.bgr + (long long)frame * p.bgr_frame_stride;
     constexpr int SW = TW + 2 * R;   // staged (used) columns per row
-    constexpr int NIT = (SW * SH + NT - 1) / NT;
     // reflect-101 only matters for tiles that touch the image border (CTA-uniform)
     const bool interior = (x0 >= R) && (y0 >= R) && (x0 + TW + R <= p.width) && (y0 + TH + R <= p.height);
-    {   // all byte loads of the thread are issued before the first use (memory-level parallelism)
-        uint32_t vb[NIT], vg[NIT], vr[NIT];
+    {   // warp w stages rows w, w + NWARP, ...; lane l columns l, l + 32, l + 64: no index division, the row pointer is
+        // warp-uniform, and all byte loads of the thread are issued before the first use (memory-level parallelism)
+        constexpr int NWARP = NT / 32, RIT = (SH + NWARP - 1) / NWARP, CIT = (SW + 31) / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        uint32_t vb[RIT][CIT], vg[RIT][CIT], vr[RIT][CIT];
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int idx = tid + it * NT;
-            vb[it] = vg[it] = vr[it] = 0u;
-            if (idx < SW * SH) {
-                int sy = idx / SW, sx = idx - sy * SW;
-                int gx = x0 - R + sx, gy = y0 - R + sy;
-                if (!interior) { gx = reflect101(gx, p.width); gy = reflect101(gy, p.height); }
-                const uint8_t* q = presmooth_row(p, src, gy) + 3 * gx;
-                vb[it] = __ldg(q); vg[it] = __ldg(q + 1); vr[it] = __ldg(q + 2);
+        for (int rr = 0; rr < RIT; ++rr) {
+            const int sy = warp + rr * NWARP;
+            int gy = y0 - R + sy;
+            if (!interior) gy = reflect101(gy, p.height);
+            const uint8_t* rowp = presmooth_row(p, src, (sy < SH) ? gy : 0);
+#pragma unroll
+            for (int k = 0; k < CIT; ++k) {
+                const int sx = lane + 32 * k;
+                vb[rr][k] = vg[rr][k] = vr[rr][k] = 0u;
+                if (sy < SH && sx < SW) {
+                    int gx = x0 - R + sx;
+                    if (!interior) gx = reflect101(gx, p.width);
+                    const uint8_t* q = rowp + 3 * gx;
+                    vb[rr][k] = __ldg(q); vg[rr][k] = __ldg(q + 1); vr[rr][k] = __ldg(q + 2);
+                }
             }
         }
 #pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int idx = tid + it * NT;
-            if (idx < SW * SH) {
-                int sy = idx / SW, sx = idx - sy * SW;
-                const int o = sy * SP + XO + sx;
-                sB[o] = (float)vb[it]; sG[o] = (float)vg[it]; sR[o] = (float)vr[it];
-                sP[o] = vb[it] | (vg[it] << 8) | (vr[it] << 16);
+        for (int rr = 0; rr < RIT; ++rr) {
+            const int sy = warp + rr * NWARP;
+#pragma unroll
+            for (int k = 0; k < CIT; ++k) {
+                const int sx = lane + 32 * k;
+                if (sy < SH && sx < SW) {
+                    const int o = sy * SP + XO + sx;
+                    sB[o] = (float)vb[rr][k]; sG[o] = (float)vg[rr][k]; sR[o] = (float)vr[rr][k];
+                    sP[o] = vb[rr][k] | (vg[rr][k] << 8) | (vr[rr][k] << 16);
+                }
             }
         }
     }
