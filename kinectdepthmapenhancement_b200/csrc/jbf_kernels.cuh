@@ -120,6 +120,10 @@ __device__ __forceinline__ int upsample_site(int x, int W, int wl) {
     return ((int)(((2LL * xl + 1) * W) / (2LL * wl)) == x) ? xl : -1;
 }
 
+// pass-1 row sums are first added plainly in groups of this many window rows, the group sums are then
+// combined error-free (2Sum); the gather-form upsampling kernel uses the same grouping
+constexpr int kRowsPer2Sum = 3;
+
 // Knuth 2Sum on both lanes: a + b == s + t exactly; a <- s, lo += t.
 __device__ __forceinline__ void two_sum2(f32x2& a, const f32x2 b, f32x2& lo) {
     const f32x2 s = add2(a, b);
@@ -315,7 +319,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     // ---------------- pass 1: spatial x colour weighted mean (JointBilateralFilter.cu:16-40)
     {
         f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull};
-        f32x2 accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};   // 2Sum low words of the row-level sums
+        f32x2 accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};   // 2Sum low words of the window sums
+        f32x2 gaccP[2] = {0ull, 0ull}, gwsP[2] = {0ull, 0ull}; // sums of the current group of rows
 #pragma unroll 1
         for (int i = 0; i < WS; ++i) {
             KDME_LOAD_ROW(sL1)
@@ -354,10 +359,17 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                     }
                 }
             }
+            // row sums -> sums of a group of kRowsPer2Sum rows (plain adds: a fraction of the window's magnitude)
+            // -> window sums (2Sum, error-free)
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-                two_sum2(accP[pr], raccP[pr], accL[pr]);
-                two_sum2(wsP[pr], rwsP[pr], wsL[pr]);
+            for (int pr = 0; pr < 2; ++pr) { gaccP[pr] = add2(gaccP[pr], raccP[pr]); gwsP[pr] = add2(gwsP[pr], rwsP[pr]); }
+            if ((i % kRowsPer2Sum) == kRowsPer2Sum - 1 || i == WS - 1) {
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    two_sum2(accP[pr], gaccP[pr], accL[pr]);
+                    two_sum2(wsP[pr], gwsP[pr], wsL[pr]);
+                    gaccP[pr] = 0ull; gwsP[pr] = 0ull;
+                }
             }
         }
         float acc[4], accl[4], wsl[4];
@@ -648,6 +660,7 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
     bool any[4];
     {
         f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull}, accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};
+        f32x2 gaccP[2] = {0ull, 0ull}, gwsP[2] = {0ull, 0ull};
         for (int sr = r_lo; sr < r_hi; ++sr) {
             const float2* lrow = reinterpret_cast<const float2*>(sL1) + (sYs[sr] - gy + R) * LPW;
             f32x2 raccP[2] = {0ull, 0ull}, rwsP[2] = {0ull, 0ull};
@@ -673,10 +686,19 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
                     rwsP[pr] = add2(rwsP[pr], ff);
                 }
             }
+            // the dense kernel's grouping: rows of the same group of kRowsPer2Sum window rows are added plainly,
+            // group sums are combined with 2Sum (groups without sites add nothing either way)
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-                two_sum2(accP[pr], raccP[pr], accL[pr]);
-                two_sum2(wsP[pr], rwsP[pr], wsL[pr]);
+            for (int pr = 0; pr < 2; ++pr) { gaccP[pr] = add2(gaccP[pr], raccP[pr]); gwsP[pr] = add2(gwsP[pr], rwsP[pr]); }
+            const int grp = (sYs[sr] - gy + R) / kRowsPer2Sum;
+            const int grp_next = (sr + 1 < r_hi) ? (sYs[sr + 1] - gy + R) / kRowsPer2Sum : -1;
+            if (grp_next != grp) {
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    two_sum2(accP[pr], gaccP[pr], accL[pr]);
+                    two_sum2(wsP[pr], gwsP[pr], wsL[pr]);
+                    gaccP[pr] = 0ull; gwsP[pr] = 0ull;
+                }
             }
         }
         float acc[4], accl[4], wsl[4];
