@@ -100,6 +100,7 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }   // both lanes negated (exact)
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     f32x2 r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
