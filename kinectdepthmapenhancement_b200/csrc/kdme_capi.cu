@@ -146,6 +146,22 @@ struct jbf_handle {
     // TMA descriptors of the last fast launch, reused while (pointers, rows, frames, box) are unchanged
     struct MapKey { const void* depth = nullptr; const void* guide = nullptr; int rows = 0, n = 0, gp = 0, bx = 0, by = 0; } map_key;
     CUtensorMap map_depth, map_guide;
+    // Second lane of the chunk loops (jbf_process_batch, jbf_process_host*): odd chunks run on an internal
+    // stream with their own guide buffer, refinement queue and TMA descriptors, so that a chunk's pre-smooth
+    // fills the tail of the previous chunk's filter and the fp64 refinement launch hides behind the next
+    // filter.  The lane's state is swapped into the fields above around each odd chunk (lane_swap).
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        uint32_t* guide4 = nullptr;
+        unsigned int* q_count_dev = nullptr;
+        int q_cur = 0;
+        unsigned int* q_items_dev = nullptr;
+        size_t q_capacity = 0;
+        MapKey map_key;
+        CUtensorMap map_depth, map_guide;
+    } alt;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool one_lane = false;
     // fused back-projection (jbf_process_xyz): set for one launch
     float* xyz_out = nullptr; float xyz_fx = 0, xyz_fy = 0; int xyz_cx = 0, xyz_cy = 0, xyz_yimg0 = 0;
     // host pipeline (jbf_process_host)
@@ -163,6 +179,41 @@ static bool fast_radius_available(int r);
 static int buf_blocks(long long n);
 
 // calcSpatialFilter -- JointBilateralFilter.cpp:31-40, fp32 on the host as the reference does.
+static void lane_swap(jbf_handle* h) {
+    jbf_handle::Lane& a = h->alt;
+    std::swap(h->stream, a.stream);
+    std::swap(h->guide4, a.guide4);
+    std::swap(h->q_count_dev, a.q_count_dev);
+    std::swap(h->q_cur, a.q_cur);
+    std::swap(h->q_items_dev, a.q_items_dev);
+    std::swap(h->q_capacity, a.q_capacity);
+    std::swap(h->map_key, a.map_key);
+    std::swap(h->map_depth, a.map_depth);
+    std::swap(h->map_guide, a.map_guide);
+}
+struct LaneScope {   // runs the enclosed launches on the alternate lane when `on`
+    jbf_handle* h; bool on;
+    LaneScope(jbf_handle* h_, bool on_) : h(h_), on(on_) { if (on) lane_swap(h); }
+    ~LaneScope() { if (on) lane_swap(h); }
+};
+static int ensure_alt_lane(jbf_handle* h) {
+    if (h->alt.stream) return KDME_OK;
+    cudaStream_t s = nullptr;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaMalloc(&h->alt.guide4, (size_t)h->max_batch * h->height * h->guide_pitch * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->alt.q_count_dev, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(h->alt.q_count_dev, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaFree(h->alt.guide4); cudaFree(h->alt.q_count_dev); cudaStreamDestroy(s);
+        h->alt.guide4 = nullptr; h->alt.q_count_dev = nullptr;
+        return fail(-(int)e, std::string("second chunk lane: ") + cudaGetErrorString(e));
+    }
+    h->alt.stream = s;
+    return KDME_OK;
+}
+
 static void host_spatial_lut(std::vector<float>& lut, int ws, float sigma_s) {
     lut.resize((size_t)ws * ws);
     for (int i = 0; i < ws; i++)
@@ -274,6 +325,7 @@ static int build_tables(jbf_handle* h) {
     h->no_refine = getenv("KDME_NO_REFINE") != nullptr;
     h->no_split_tiles = getenv("KDME_NO_SPLIT_TILES") != nullptr;
     h->no_pdl = getenv("KDME_NO_PDL") != nullptr;
+    h->one_lane = getenv("KDME_ONE_LANE") != nullptr;
     if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
     if (const char* rl = getenv("KDME_RES_LIMIT")) h->res_limit = atoi(rl);
     h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
@@ -356,6 +408,12 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->stats_dev);
     cudaFree(h->q_count_dev);
     cudaFree(h->q_items_dev);
+    cudaFree(h->alt.guide4);
+    cudaFree(h->alt.q_count_dev);
+    cudaFree(h->alt.q_items_dev);
+    if (h->alt.stream) cudaStreamDestroy(h->alt.stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaFree(h->ltab_generic_dev);
     cudaFree(h->ltab_generic1_dev);
     cudaFree(h->ps_space_dev);
@@ -749,13 +807,27 @@ extern "C" int jbf_process_batch(jbf_handle* h, const float* depth_dev, const ui
     if (bgr_step == 0) bgr_step = (size_t)3 * h->width;
     DeviceGuard g(h->device);
     const size_t plane = (size_t)h->width * h->height;
-    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch) {
+    // more than one chunk: alternate the chunks between the caller's stream and the internal lane
+    const bool two = n_frames > h->max_batch && !h->one_lane && h->fast;
+    if (two) {
+        int rc = ensure_alt_lane(h);
+        if (rc != KDME_OK) return rc;
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->alt.stream, h->ev_fork, 0));
+    }
+    int chunk = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += h->max_batch, ++chunk) {
         const int n = (n_frames - f0 < h->max_batch) ? (n_frames - f0) : h->max_batch;
+        LaneScope lane(h, two && (chunk & 1));
         int rc = launch_presmooth(h, bgr_dev + (size_t)f0 * bgr_step * h->height, bgr_step, h->guide4, h->guide_pitch, n);
         if (rc != KDME_OK) return rc;
         rc = launch_filter(h, depth_dev + (size_t)f0 * plane, h->guide4, h->guide_pitch, out_dev + (size_t)f0 * plane, n,
                            kStagePlain, nullptr, 0, 0, -1, 0, -1, nullptr, nullptr, 0, 0, /*pdl=*/true);
         if (rc != KDME_OK) return rc;
+    }
+    if (two) {   // the caller's stream continues when both lanes are done
+        CK(cudaEventRecord(h->ev_join, h->alt.stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     return KDME_OK;
 }
@@ -850,10 +922,19 @@ static int process_host_impl(jbf_handle* h, const float* depth_host, const uint1
     if (depth16_host)
         for (int b = 0; b < kPipeDepth; b++)
             if (!h->pipe_depth16[b]) CK(cudaMalloc(&h->pipe_depth16[b], plane * h->pipe_chunk * sizeof(uint16_t)));
+    // compute of odd chunks runs on the internal lane (own stream, guide buffer and refinement queue)
+    const bool two = n_frames > h->pipe_chunk && !h->one_lane && h->fast;
+    if (two) {
+        rc = ensure_alt_lane(h);
+        if (rc != KDME_OK) return rc;
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->alt.stream, h->ev_fork, 0));
+    }
     int chunk = 0;
     for (int f0 = 0; f0 < n_frames; f0 += h->pipe_chunk, ++chunk) {
         const int n = (n_frames - f0 < h->pipe_chunk) ? (n_frames - f0) : h->pipe_chunk;
         const int b = chunk % kPipeDepth;
+        LaneScope lane(h, two && (chunk & 1));
         if (chunk >= kPipeDepth) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_done[b], 0));  // slot inputs consumed
         if (depth16_host)
             CK(cudaMemcpyAsync(h->pipe_depth16[b], depth16_host + (size_t)f0 * plane, plane * n * sizeof(uint16_t),
@@ -883,6 +964,7 @@ static int process_host_impl(jbf_handle* h, const float* depth_host, const uint1
         CK(cudaEventRecord(h->ev_free[b], h->s_d2h));
     }
     CK(cudaStreamSynchronize(h->s_d2h));
+    if (two) CK(cudaStreamSynchronize(h->alt.stream));
     CK(cudaStreamSynchronize(h->stream));
     return KDME_OK;
 }

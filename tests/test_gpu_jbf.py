@@ -304,6 +304,35 @@ def test_process_host_pipeline_matches_device_path():
     assert torch.equal(oh, want)
 
 
+def test_two_lane_chunk_pipeline_bit_identical_and_repeatable(monkeypatch):
+    """jbf_process_batch / jbf_process_host alternate their chunks between the caller's stream and an internal lane
+    (own guide buffer, refinement queue, TMA descriptors).  The lanes must change nothing: same bits and the same
+    refinement counts as the single-lane order (KDME_ONE_LANE=1), call after call."""
+    from kinectdepthmapenhancement_b200 import synth
+    n, w, h = 11, 320, 240
+    depth, bgr = synth.rgbd_stream(n, w, h, seed=8)          # this seed's frames hold ill-conditioned pixels
+    JBF = _jbf_cls()
+    monkeypatch.setenv("KDME_ONE_LANE", "1")
+    f1 = JBF(w, h, window_radius=7, max_batch=2)
+    monkeypatch.delenv("KDME_ONE_LANE")
+    f2 = JBF(w, h, window_radius=7, max_batch=2)              # 2+2+2+2+2+1: six chunks, three per lane
+    d, c = depth.cuda(), bgr.cuda()
+    want = f1.process_batch(d, c).cpu()
+    stats1 = f1.refine_stats()
+    assert stats1[0] > 0 and stats1[1] == 0
+    for _ in range(3):
+        got = f2.process_batch(d, c).cpu()
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+        assert f2.refine_stats() == stats1
+    # a single-frame call on the same handle right after (caller's lane only) still matches
+    f2.Process(d[4], c[4])
+    assert torch.equal(f2.getFiltered_Device().cpu().view(torch.int32), want[4].view(torch.int32))
+    dh, ch = depth.pin_memory(), bgr.pin_memory()
+    oh = torch.empty_like(depth).pin_memory()
+    f2.process_host(dh, ch, oh)
+    assert torch.equal(oh.view(torch.int32), want.view(torch.int32))
+
+
 def test_pitched_gpumat_step_is_honoured():
     """cv::gpu::GpuMat rows may be padded (step > 3*width); the reference ignores step (it indexes
     (y*W+x)*3, JointBilateralFilter.cu:22-24) and only works for continuous images.  Through the C ABI a
