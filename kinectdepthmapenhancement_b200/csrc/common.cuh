@@ -29,8 +29,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, max relative error 2^-23
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {   // ld.shared through a 32-bit shared-window address
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 // ---- mbarrier + TMA (cp.async.bulk.tensor) primitives -------------------------

@@ -64,6 +64,8 @@ struct JbfParams {
     int mode;                    // StageMode
     const float* depth_lo;       // upsample: low-res depth [hl][wl]
     int wl, hl;
+    const int* ups_inv_x;        // upsample, optional: low-res column landing on high-res column x, or -1 ([width]); null = compute
+    const int* ups_inv_y;        // same for rows ([height])
     // row-band mode: the arrays hold `height` rows (band + halos); output rows are
     // [y_off, y_off + out_rows) of them and `out` holds only those.  Results do not depend on where
     // tiles start vertically, so a band equals the same rows of the whole image bit for bit.
@@ -613,71 +615,116 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
 // same order (taps that are not sites have weight exactly 0 there and add nothing), so the result equals
 // jbf_fast_kernel on the materialised sparse image BIT FOR BIT -- including the accumulation origin rule,
 // the 2Sum row partials and the fp64 refinement queue.
+// padding of a pair-table row of the gather kernel: entries for window columns -2 .. WS+4 (WS + 7 is even, so a
+// table is a whole number of 16-byte words)
+constexpr int kUpsPad = 7;
+
 struct UpsampleGeom {
     int ncol_max, nrow_max;      // staged site columns / rows per tile (host-computed bound)
     int radius;
-    const float* ltab1;          // [(2r+1)][(2r+1)] log2(S)+bias1   (pass 1)
-    const float* ltab2;          // [(2r+1)][(2r+1)] log2(S)+kWeightBias (pass 2)
+    const float* ltab1;          // padded pair table [(2r+1)][(2r+1) + kUpsPad][2], bias1 (pass 1); see the kernel
+    const float* ltab2;          // same, bias kWeightBias (pass 2)
+    // the lattice, tabulated once per (wl, hl) on the host (no 64-bit divisions in the kernel):
+    const int* site_x;           // [wl] high-res x of low-res column xl
+    const int* site_y;           // [hl]
+    const int* tile_xl;          // [tiles_x][2] = first low-res column with site >= x0 - r, first with site > x0 + TW - 1 + r
+    const int* tile_yl;          // [tiles_y][2]
 };
 
-// first low-res index whose site is >= x
-__device__ __forceinline__ int upsample_first_site_at_or_after(int x, int W, int wl) {
+// first low-res index whose site is >= x (wl when every site lies below x)
+__host__ __device__ __forceinline__ int upsample_first_site_at_or_after(int x, int W, int wl) {
     if (x <= 0) return 0;
     long long num = 2LL * wl * x - W;                       // site(xl) >= x  <=>  (2xl+1) W >= 2 wl x  (floor is monotone)
     int xl = (num <= 0) ? 0 : (int)((num + 2LL * W - 1) / (2LL * W));
     while (xl > 0 && (int)(((2LL * (xl - 1) + 1) * W) / (2LL * wl)) >= x) --xl;
     while (xl < wl && (int)(((2LL * xl + 1) * W) / (2LL * wl)) < x) ++xl;
-    return xl;
+    return xl < wl ? xl : wl;   // wl: no such site
 }
 
-template <int TW, int TH>
-__global__ void __launch_bounds__((TW / 4) * TH)
+// One site seen by a thread's two pixel pairs, pass 1 / pass 2 (the dense kernel's packed tap, LUT pair from the
+// padded table; lp points at pair 0's entry, pair 1's is two entries below)
+__device__ __forceinline__ void gather_site_p1(const uint32_t (&gp)[4], float d, uint32_t gq, const float2* lp, float sq,
+                                               float ncO, f32x2 nkc2, f32x2 (&raccP)[2], f32x2 (&rwsP)[2]) {
+    const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+    const uint32_t mq = (d != 0.f) ? kMagicValid : kMagicInvalid;
+    const float dsh = fmaf(d, sq, ncO);
+    const f32x2 dsh2 = pack2(dsh, dsh);
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+        const float2 l2 = lp[-2 * pr];
+        const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
+        const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, mq)), __uint_as_float(__dp4a(ad1, ad1, mq)));
+        const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(l2.x, l2.y));
+        float a0, a1;
+        unpack2(ar, a0, a1);
+        const f32x2 ff = pack2(ex2_approx(a0), ex2_approx(a1));
+        raccP[pr] = fma2(ff, dsh2, raccP[pr]);
+        rwsP[pr] = add2(rwsP[pr], ff);
+    }
+}
+__device__ __forceinline__ void gather_site_p2(const uint32_t (&gp)[4], float d, uint32_t gq, const float2* lp, float sq,
+                                               float ncO, f32x2 nkc2, const f32x2 (&ndelP)[2], float e_thr,
+                                               f32x2 (&rnumP)[2], f32x2 (&rdenP)[2]) {
+    const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+    const uint32_t mq = (d != 0.f) ? kMagicValid : kMagicInvalid;
+    const float dsh = fmaf(d, sq, ncO);
+    const f32x2 dsh2 = pack2(dsh, dsh);
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) {
+        const float2 l2 = lp[-2 * pr];
+        const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
+        const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, mq)), __uint_as_float(__dp4a(ad1, ad1, mq)));
+        const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(l2.x, l2.y));
+        const f32x2 ee = add2(dsh2, ndelP[pr]);
+        float a0, a1, e0, e1;
+        unpack2(ar, a0, a1);
+        unpack2(ee, e0, e1);
+        if (!(fabsf(e0) > e_thr)) a0 = fmaf(-e0, e0, a0);
+        if (!(fabsf(e1) > e_thr)) a1 = fmaf(-e1, e1, a1);
+        const f32x2 ff = pack2(ex2_approx(a0), ex2_approx(a1));
+        rnumP[pr] = fma2(ff, ee, rnumP[pr]);
+        rdenP[pr] = add2(rdenP[pr], ff);
+    }
+}
+
+// MAXC > 0: no thread sees more than MAXC site columns (host-computed: ceil((2r+4) wl / W)); the columns are then
+// resolved once per thread into registers and every site row is a straight-line body of MAXC sites (a missing
+// column reads a staged site with an out-of-window table entry: weight exactly 0).  MAXC == 0: runtime column loop.
+template <int TW, int TH, int MAXC>
+__global__ void __launch_bounds__((TW / 4) * TH, 3)
 jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
     constexpr int NT = (TW / 4) * TH;
     const int R = g.radius, WS = 2 * R + 1;
+    // pair tables, one row per window row: entry e = jj + 2 holds {Lx[jj], Lx[jj-1]} for jj = -2 .. WS+4, where
+    // Lx[j] = log2 spatial weight for 0 <= j < WS and -3e38 outside the window (2^(-3e38 + ...) == 0 exactly under
+    // ex2.approx.ftz): a lane whose column falls outside the window gets weight 0 from the table itself, so the tap
+    // needs neither a clamp nor a predicate.  Built once per handle on the host (kUpsPad), copied here 16 bytes at a time.
+    const int LPW = WS + kUpsPad;
     extern __shared__ __align__(16) uint8_t smem_up[];
-    float* sSd = reinterpret_cast<float*>(smem_up);                      // [nrow_max][ncol_max] sample depth (0 = hole)
+    float* sL1 = reinterpret_cast<float*>(smem_up);                      // [WS][LPW][2], WS * LPW * 2 is a multiple of 4
+    float* sL2 = sL1 + WS * LPW * 2;
+    float* sSd = sL2 + WS * LPW * 2;                                     // [nrow_max][ncol_max] sample depth (0 = hole)
     uint32_t* sSg = reinterpret_cast<uint32_t*>(sSd + g.nrow_max * g.ncol_max);   // guide word at the site
     int* sXs = reinterpret_cast<int*>(sSg + g.nrow_max * g.ncol_max);    // [ncol_max] site x
     int* sYs = sXs + g.ncol_max;                                         // [nrow_max] site y
-    float* sL1 = reinterpret_cast<float*>(sYs + g.nrow_max + ((g.ncol_max + g.nrow_max) & 1));   // [WS][WS+1] pairs {L[jj], L[jj-1]} (8-byte aligned)
-    float* sL2 = sL1 + WS * (WS + 1) * 2;
-    __shared__ int sN[2];
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    for (int idx = tid; idx < WS * (WS + 1); idx += NT) {   // padded pair tables from the plain [WS][WS] ones
-        const int i = idx / (WS + 1), jj = idx - i * (WS + 1);
-        const float a1 = (jj < WS) ? __ldg(g.ltab1 + i * WS + jj) : 0.f, b1 = (jj > 0) ? __ldg(g.ltab1 + i * WS + jj - 1) : 0.f;
-        const float a2 = (jj < WS) ? __ldg(g.ltab2 + i * WS + jj) : 0.f, b2 = (jj > 0) ? __ldg(g.ltab2 + i * WS + jj - 1) : 0.f;
-        sL1[2 * idx] = a1; sL1[2 * idx + 1] = b1;
-        sL2[2 * idx] = a2; sL2[2 * idx + 1] = b2;
+    for (int idx = tid; idx < WS * LPW / 2; idx += NT) {
+        reinterpret_cast<float4*>(sL1)[idx] = __ldg(reinterpret_cast<const float4*>(g.ltab1) + idx);
+        reinterpret_cast<float4*>(sL2)[idx] = __ldg(reinterpret_cast<const float4*>(g.ltab2) + idx);
     }
     grid_dependency_wait();
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.q_count_prev = 0u;
     // site columns with x in [x0 - R, x0 + TW - 1 + R], site rows with y in [y0 - R, y0 + TH - 1 + R]
-    const int xl0 = upsample_first_site_at_or_after(x0 - R, p.width, p.wl);
-    const int yl0 = upsample_first_site_at_or_after(y0 - R, p.height, p.hl);
-    for (int t = tid; t < g.ncol_max + g.nrow_max; t += NT) {
-        if (t < g.ncol_max) {
-            const int xl = xl0 + t;
-            const int xs = (xl < p.wl) ? (int)(((2LL * xl + 1) * p.width) / (2LL * p.wl)) : 0x3fffffff;
-            sXs[t] = (xs <= x0 + TW - 1 + R) ? xs : 0x3fffffff;
-        } else {
-            const int yl = yl0 + (t - g.ncol_max);
-            const int ys = (yl < p.hl) ? (int)(((2LL * yl + 1) * p.height) / (2LL * p.hl)) : 0x3fffffff;
-            sYs[t - g.ncol_max] = (ys <= y0 + TH - 1 + R) ? ys : 0x3fffffff;
-        }
+    const int xl0 = __ldg(g.tile_xl + 2 * blockIdx.x), yl0 = __ldg(g.tile_yl + 2 * blockIdx.y);
+    const int ncol = min(__ldg(g.tile_xl + 2 * blockIdx.x + 1) - xl0, g.ncol_max);
+    const int nrow = min(__ldg(g.tile_yl + 2 * blockIdx.y + 1) - yl0, g.nrow_max);
+    for (int t = tid; t < ncol + nrow; t += NT) {
+        if (t < ncol) sXs[t] = __ldg(g.site_x + xl0 + t);
+        else sYs[t - ncol] = __ldg(g.site_y + yl0 + (t - ncol));
     }
     __syncthreads();
-    if (tid == 0) {
-        int nc = 0, nr = 0;
-        while (nc < g.ncol_max && sXs[nc] != 0x3fffffff) ++nc;
-        while (nr < g.nrow_max && sYs[nr] != 0x3fffffff) ++nr;
-        sN[0] = nc; sN[1] = nr;
-    }
-    __syncthreads();
-    const int ncol = sN[0], nrow = sN[1];
     for (int idx = tid; idx < ncol * nrow; idx += NT) {
         const int sr = idx / ncol, sc = idx - sr * ncol;
         const float d = __ldg(p.depth_lo + (long long)(yl0 + sr) * p.wl + (xl0 + sc));
@@ -695,10 +742,16 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
             if (gx + k < p.width) gp[k] = __ldg(p.guide4 + (long long)gy * p.guide_pitch + gx + k);
     }
     // this thread's site rows [r_lo, r_hi) and site columns [c_lo, c_hi) (union over its 4 pixels)
+    // (the lattice is near-uniform: start from the proportional guess and correct by a step or two instead of
+    // scanning the staged lists from their first entry)
     int r_lo = 0, r_hi = 0, c_lo = 0, c_hi = 0;
+    if (nrow > 0) r_lo = min(max((int)floorf((float)(gy - R - sYs[0]) * ((float)p.hl / (float)p.height)), 0), nrow);
+    if (ncol > 0) c_lo = min(max((int)floorf((float)(gx - R - sXs[0]) * ((float)p.wl / (float)p.width)), 0), ncol);
+    while (r_lo > 0 && sYs[r_lo - 1] >= gy - R) --r_lo;
     while (r_lo < nrow && sYs[r_lo] < gy - R) ++r_lo;
     r_hi = r_lo;
     while (r_hi < nrow && sYs[r_hi] <= gy + R) ++r_hi;
+    while (c_lo > 0 && sXs[c_lo - 1] >= gx - R) --c_lo;
     while (c_lo < ncol && sXs[c_lo] < gx - R) ++c_lo;
     c_hi = c_lo;
     while (c_hi < ncol && sXs[c_hi] <= gx + 3 + R) ++c_hi;
@@ -727,46 +780,50 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
     const float nkc = p.nkc;
 
     // Branch-free taps in the dense kernel's packed form: pixels (0,1) and (2,3) share a site, lane 0 of a pair
-    // sees it at window column j0 and lane 1 at j0 - 1; a lane whose column falls outside the window (or a site
-    // that is a hole) gets weight exactly 0, which adds nothing -- the sums are the dense kernel's, bit for bit.
-    const f32x2 kNeg23 = pack2(-8388608.0f, -8388608.0f);
+    // sees it at window column j0 and lane 1 at j0 - 1.  A lane whose column falls outside the window reads -3e38
+    // from the padded table, a site that is a hole carries the invalid magic in the IDP.4A accumulator (as in the
+    // dense kernel): either way the weight is exactly 0 and adds nothing -- the sums are the dense kernel's, bit for bit.
     const f32x2 nkc2 = pack2(nkc, nkc);
-    const int LPW = WS + 1;   // padded pair-table row: entry jj = {L[jj], L[jj-1]}, jj = 0..WS
+    const int ncm = g.ncol_max;
+    const int jofs = R + 2 - gx;              // table entry of pair 0 for a site at x: x + jofs; pair 1: two less
+    // the thread's site columns, resolved once: staged column and table entry (a missing column: any staged
+    // column -- its data is finite -- with the all-out-of-window entry WS + 5, whose pair-1 partner WS + 3 is too)
+    int scol[MAXC > 0 ? MAXC : 1], eoff[MAXC > 0 ? MAXC : 1];
+    if constexpr (MAXC > 0) {
+        if (ncol == 0) r_hi = r_lo;           // no staged site at all: nothing to sweep
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int sc = c_lo + c;
+            const bool ok = sc < c_hi;
+            scol[c] = ok ? sc : min(c_lo, max(ncol - 1, 0));
+            eoff[c] = ok ? sXs[ok ? sc : 0] + jofs : WS + 5;   // entries WS + 5 and WS + 3: all four columns outside
+        }
+    }
     float wsum[4], delta[4];
     bool any[4];
     {
         f32x2 accP[2] = {0ull, 0ull}, wsP[2] = {0ull, 0ull}, accL[2] = {0ull, 0ull}, wsL[2] = {0ull, 0ull};
         f32x2 gaccP[2] = {0ull, 0ull}, gwsP[2] = {0ull, 0ull};
         for (int sr = r_lo; sr < r_hi; ++sr) {
-            const float2* lrow = reinterpret_cast<const float2*>(sL1) + (sYs[sr] - gy + R) * LPW;
+            const int wrow = sYs[sr] - gy + R;
+            const float2* lrow = reinterpret_cast<const float2*>(sL1) + wrow * LPW;
+            const float* drow = sSd + sr * ncm;
+            const uint32_t* grow = sSg + sr * ncm;
             f32x2 raccP[2] = {0ull, 0ull}, rwsP[2] = {0ull, 0ull};
-            for (int sc = c_lo; sc < c_hi; ++sc) {
-                const float d = sSd[sr * g.ncol_max + sc];
-                const bool valid = d != 0.f;
-                const uint32_t gq = sSg[sr * g.ncol_max + sc];
-                const float dsh = fmaf(d, sq, ncO);
-                const f32x2 dsh2 = pack2(dsh, dsh);
-                const int jb = sXs[sc] - gx + R;
+            if constexpr (MAXC > 0) {
 #pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                    const int j0 = jb - 2 * pr;
-                    const bool m0 = valid & ((unsigned)j0 < (unsigned)WS), m1 = valid & ((unsigned)(j0 - 1) < (unsigned)WS);
-                    const float2 lp = lrow[min(max(j0, 0), WS)];
-                    const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
-                    const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, kMagicValid)), __uint_as_float(__dp4a(ad1, ad1, kMagicValid)));
-                    const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(lp.x, lp.y));
-                    float a0, a1;
-                    unpack2(ar, a0, a1);
-                    const f32x2 ff = pack2(m0 ? ex2_approx(a0) : 0.f, m1 ? ex2_approx(a1) : 0.f);
-                    raccP[pr] = fma2(ff, dsh2, raccP[pr]);
-                    rwsP[pr] = add2(rwsP[pr], ff);
-                }
+                for (int c = 0; c < MAXC; ++c)
+                    gather_site_p1(gp, drow[scol[c]], grow[scol[c]], lrow + eoff[c], sq, ncO, nkc2, raccP, rwsP);
+            } else {
+#pragma unroll 2
+                for (int sc = c_lo; sc < c_hi; ++sc)
+                    gather_site_p1(gp, drow[sc], grow[sc], lrow + sXs[sc] + jofs, sq, ncO, nkc2, raccP, rwsP);
             }
             // the dense kernel's grouping: rows of the same group of kRowsPer2Sum window rows are added plainly,
             // group sums are combined with 2Sum (groups without sites add nothing either way)
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) { gaccP[pr] = add2(gaccP[pr], raccP[pr]); gwsP[pr] = add2(gwsP[pr], rwsP[pr]); }
-            const int grp = (sYs[sr] - gy + R) / kRowsPer2Sum;
+            const int grp = wrow / kRowsPer2Sum;
             const int grp_next = (sr + 1 < r_hi) ? (sYs[sr + 1] - gy + R) / kRowsPer2Sum : -1;
             if (grp_next != grp) {
 #pragma unroll
@@ -799,32 +856,17 @@ jbf_upsample_gather_kernel(const JbfParams p, const UpsampleGeom g) {
         f32x2 numP[2] = {0ull, 0ull}, denP[2] = {0ull, 0ull};
         for (int sr = r_lo; sr < r_hi; ++sr) {
             const float2* lrow = reinterpret_cast<const float2*>(sL2) + (sYs[sr] - gy + R) * LPW;
+            const float* drow = sSd + sr * ncm;
+            const uint32_t* grow = sSg + sr * ncm;
             f32x2 rnumP[2] = {0ull, 0ull}, rdenP[2] = {0ull, 0ull};
-            for (int sc = c_lo; sc < c_hi; ++sc) {
-                const float d = sSd[sr * g.ncol_max + sc];
-                const bool valid = d != 0.f;
-                const uint32_t gq = sSg[sr * g.ncol_max + sc];
-                const float dsh = fmaf(d, sq, ncO);
-                const f32x2 dsh2 = pack2(dsh, dsh);
-                const int jb = sXs[sc] - gx + R;
+            if constexpr (MAXC > 0) {
 #pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                    const int j0 = jb - 2 * pr;
-                    const bool m0 = valid & ((unsigned)j0 < (unsigned)WS), m1 = valid & ((unsigned)(j0 - 1) < (unsigned)WS);
-                    const float2 lp = lrow[min(max(j0, 0), WS)];
-                    const uint32_t ad0 = __vabsdiffu4(gp[2 * pr], gq), ad1 = __vabsdiffu4(gp[2 * pr + 1], gq);
-                    const f32x2 xx = pack2(__uint_as_float(__dp4a(ad0, ad0, kMagicValid)), __uint_as_float(__dp4a(ad1, ad1, kMagicValid)));
-                    const f32x2 ar = fma2(add2(xx, kNeg23), nkc2, pack2(lp.x, lp.y));
-                    const f32x2 ee = add2(dsh2, ndelP[pr]);
-                    float a0, a1, e0, e1;
-                    unpack2(ar, a0, a1);
-                    unpack2(ee, e0, e1);
-                    if (!(fabsf(e0) > e_thr)) a0 = fmaf(-e0, e0, a0);
-                    if (!(fabsf(e1) > e_thr)) a1 = fmaf(-e1, e1, a1);
-                    const f32x2 ff = pack2(m0 ? ex2_approx(a0) : 0.f, m1 ? ex2_approx(a1) : 0.f);
-                    rnumP[pr] = fma2(ff, ee, rnumP[pr]);
-                    rdenP[pr] = add2(rdenP[pr], ff);
-                }
+                for (int c = 0; c < MAXC; ++c)
+                    gather_site_p2(gp, drow[scol[c]], grow[scol[c]], lrow + eoff[c], sq, ncO, nkc2, ndelP, e_thr, rnumP, rdenP);
+            } else {
+#pragma unroll 2
+                for (int sc = c_lo; sc < c_hi; ++sc)
+                    gather_site_p2(gp, drow[sc], grow[sc], lrow + sXs[sc] + jofs, sq, ncO, nkc2, ndelP, e_thr, rnumP, rdenP);
             }
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) { numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
@@ -903,7 +945,8 @@ __device__ __forceinline__ void warp_sum2_f64(double& a, double& b) {
 
 __device__ __forceinline__ float jbf_sample_depth(const JbfParams& p, int frame, int gx, int gy) {
     if (p.mode == kStageUpsample) {
-        const int xl = upsample_site(gx, p.width, p.wl), yl = upsample_site(gy, p.height, p.hl);
+        const int xl = p.ups_inv_x ? __ldg(p.ups_inv_x + gx) : upsample_site(gx, p.width, p.wl);
+        const int yl = p.ups_inv_y ? __ldg(p.ups_inv_y + gy) : upsample_site(gy, p.height, p.hl);
         return ((xl >= 0) & (yl >= 0)) ? __ldg(p.depth_lo + (long long)yl * p.wl + xl) : 0.f;
     }
     const float* row = p.depth + (long long)frame * p.depth_frame_stride + (long long)gy * p.width;
@@ -916,14 +959,16 @@ __device__ __forceinline__ float jbf_sample_depth(const JbfParams& p, int frame,
 // reduction (n = nearest integer, |f| <= 0.5) and the degree-11 Taylor polynomial of e^(f ln2) (truncation
 // < 1e-14 relative), exponent attached by integer add.  Arguments beyond the double range return 0.
 __device__ __forceinline__ double exp_neg_f64(double x) {
-    const double t = -x * 1.4426950408889634;                 // log2 domain, <= 0
-    if (t < -1000.0) return 0.0;
+    // branch-free (the out-of-range case is a clamp + select): the caller's unrolled taps then form independent
+    // straight-line chains the scheduler can interleave -- the kernel is bound by the latency of these chains
+    const double t0 = -x * 1.4426950408889634;                // log2 domain, <= 0
+    const bool tiny = t0 < -1000.0;
+    const double t = tiny ? -1000.0 : t0;
     const double kMagic = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
     const double tn = t + kMagic;
     const int n = __double2loint(tn);
     const double f = (t - (tn - kMagic)) * 0.6931471805599453; // natural-log units, |f| <= 0.3466
-    // Estrin evaluation of sum_{k=0..11} f^k / k! (dependency depth 5 instead of 11: the refinement kernel is
-    // latency-bound on its fp64 chains)
+    // Estrin evaluation of sum_{k=0..11} f^k / k! (dependency depth 5 instead of 11)
     const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
     const double q0 = fma(f, 1.0, 1.0);                                            // 1/0! + f/1!
     const double q1 = fma(f, 1.666666666666667e-01, 0.5);                          // 1/2! + f/3!
@@ -934,11 +979,13 @@ __device__ __forceinline__ double exp_neg_f64(double x) {
     const double r0 = fma(q1, f2, q0), r1 = fma(q3, f2, q2), r2 = fma(q5, f2, q4);
     double p = fma(r1, f4, r0);
     p = fma(r2, f8, p);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return tiny ? 0.0 : r;
 }
 
 // KMAX = taps per lane the instantiation can hold: (2r+1)^2 <= 32 * KMAX
-template <int KMAX>
+// PLAIN = whole-frame / local-band depth plane (no upsampling lattice, no peer-memory halos): direct loads
+template <int KMAX, bool PLAIN>
 __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, const int radius) {
     const int lane = threadIdx.x & 31;
     const int ws = 2 * radius + 1, ntap = ws * ws;
@@ -968,12 +1015,11 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
     unsigned idx_next = (first < p.q_capacity) ? p.q_items[first] : 0u;
     const unsigned pushed = *reinterpret_cast<volatile unsigned int*>(p.q_count);
     const unsigned count = pushed < p.q_capacity ? pushed : p.q_capacity;
-    const bool plain = (p.mode != kStageUpsample) && p.depth_up == nullptr && p.depth_dn == nullptr;
+    const unsigned per_frame = (unsigned)p.out_rows * (unsigned)p.width;
     for (unsigned item = first; item < count; item += nwarps) {
         unsigned idx = idx_next;
         if (idx >= total_px) idx = total_px - 1;
         if (item + nwarps < count) idx_next = p.q_items[item + nwarps];
-        const unsigned per_frame = (unsigned)p.out_rows * (unsigned)p.width;
         const int frame = (int)(idx / per_frame);
         const unsigned rem = idx - (unsigned)frame * per_frame;
         const int oy = (int)(rem / (unsigned)p.width), x = (int)(rem - (unsigned)oy * (unsigned)p.width);
@@ -990,11 +1036,13 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
             const int ty = y + tdy[u], tx = x + tdx[u];
             const bool in = tx >= 0 && tx < p.width && ty >= 0 && ty < p.height;
             const int cy_ = in ? ty : y, cx_ = in ? tx : x;
-            const float df = plain ? __ldg(dsrc + (long long)cy_ * p.width + cx_) : jbf_sample_depth(p, frame, cx_, cy_);
+            const float df = PLAIN ? __ldg(dsrc + (long long)cy_ * p.width + cx_) : jbf_sample_depth(p, frame, cx_, cy_);
             gql[u] = __ldg(gsrc + (long long)cy_ * p.guide_pitch + cx_);
             dfl[u] = in ? df : 0.f;
         }
-        // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight
+        // each lane keeps its taps in registers between the two passes: depth and the spatial x colour weight.
+        // Both passes are straight-line per tap (selects, no branches), so the KMAX exponentials of a lane are
+        // independent chains in flight together.
         double dl[KMAX], fl[KMAX];
         double a = 0.0, wt = 0.0;
 #pragma unroll
@@ -1002,29 +1050,29 @@ __global__ void __launch_bounds__(128) jbf_refine_kernel(const JbfParams p, cons
             const bool v = dfl[u] > kValidDepth;
             const uint32_t ad = __vabsdiffu4(gpix, gql[u]);
             const double cd = (double)__dp4a(ad, ad, 0u);
-            const double f = v ? tsw[u] * exp_neg_f64(cd * p.kc) : 0.0;
+            const double w = tsw[u] * exp_neg_f64(cd * p.kc);
+            const double f = v ? w : 0.0;
             dl[u] = v ? (double)dfl[u] : 0.0;
             fl[u] = f;
-            a += dl[u] * f;
+            a = fma(dl[u], f, a);
             wt += f;
         }
         warp_sum2_f64(a, wt);
-        float r = 0.f;
-        if (wt > 0.0) {
-            const double m = a / wt;
-            double num = 0.0, den = 0.0;
+        // wt == 0 (no valid tap): every fl is 0, the pass below yields den == 0 -> output 0 (m is unused garbage-free)
+        const double m = (wt > 0.0) ? a / wt : 0.0;
+        double num = 0.0, den = 0.0;
 #pragma unroll
-            for (int u = 0; u < KMAX; ++u) {
-                double f = fl[u];
-                const double e = dl[u] - m;
-                const double q = e * e * p.kd;
-                if (q <= kExpZeroArg) f *= exp_neg_f64(q);   // else fp32 expf() == 0: factor skipped (.cu:67-68)
-                num += dl[u] * f;
-                den += f;
-            }
-            warp_sum2_f64(num, den);
-            r = (den == 0.0) ? 0.f : (float)(num / den);
+        for (int u = 0; u < KMAX; ++u) {
+            const double e = dl[u] - m;
+            const double q = e * e * p.kd;
+            const bool keep = q <= kExpZeroArg;               // else fp32 expf() == 0: factor skipped (.cu:67-68)
+            const double g = exp_neg_f64(keep ? q : 0.0);
+            const double f = keep ? fl[u] * g : fl[u];
+            num = fma(dl[u], f, num);
+            den += f;
         }
+        warp_sum2_f64(num, den);
+        const float r = (den == 0.0) ? 0.f : (float)(num / den);
         if (lane == 0) {
             p.out[idx] = r;
             if (p.xyz != nullptr) {

@@ -135,7 +135,8 @@ struct jbf_handle {
     float bias1 = 0.f, flag_scale = 0.f;
     double kc = 0, kd = 0;
     float* ltab_generic_dev = nullptr;  // [WS][WS], bias kWeightBias
-    float* ltab_generic1_dev = nullptr; // [WS][WS], bias bias1 (pass 1 of the gather-form upsampling)
+    float* ltab_generic1_dev = nullptr; // [WS][WS], bias bias1
+    float *ltab_ups1_dev = nullptr, *ltab_ups2_dev = nullptr;   // padded pair tables of the gather-form upsampling
     // derived
     bool fast = false;
     float nkc = 0, sq = 1, inv_sq = 1, e_thr = 0;
@@ -161,6 +162,9 @@ struct jbf_handle {
         CUtensorMap map_depth, map_guide;
     } alt;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // gather-form upsampling: the site lattice tabulated for (ups_wl, ups_hl, ups_rows): site_x[wl], site_y[hl],
+    // tile_xl[tiles_x][2], tile_yl[tiles_y][2]
+    int* ups_tab_dev = nullptr; int ups_wl = 0, ups_hl = 0, ups_rows = 0;
     bool one_lane = false;
     // fused back-projection (jbf_process_xyz): set for one launch
     float* xyz_out = nullptr; float xyz_fx = 0, xyz_fy = 0; int xyz_cx = 0, xyz_cy = 0, xyz_yimg0 = 0;
@@ -274,6 +278,28 @@ static int build_tables(jbf_handle* h) {
         }
         CK(cudaMalloc(&h->ltab_generic1_dev, lg1.size() * sizeof(float)));
         CK(cudaMemcpy(h->ltab_generic1_dev, lg1.data(), lg1.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {   // gather-form upsampling: padded pair tables (see jbf_upsample_gather_kernel)
+        const int lpw = ws + kUpsPad;
+        std::vector<float> t1((size_t)ws * lpw * 2), t2(t1.size());
+        const float kOut = -3.0e38f;
+        for (int i = 0; i < ws; i++)
+            for (int e = 0; e < lpw; e++) {
+                const int jj = e - 2;
+                const bool ina = jj >= 0 && jj < ws, inb = jj >= 1 && jj <= ws;
+                const float sa = ina ? lut[(size_t)i * ws + jj] : 0.f, sb = inb ? lut[(size_t)i * ws + jj - 1] : 0.f;
+                auto lg2 = [&](float sv, float bias) {
+                    return (sv != 0.0f && std::isfinite(sv)) ? (float)(std::log2((double)sv) + (double)bias) : bias;
+                };
+                t1[((size_t)i * lpw + e) * 2 + 0] = ina ? lg2(sa, h->bias1) : kOut;
+                t1[((size_t)i * lpw + e) * 2 + 1] = inb ? lg2(sb, h->bias1) : kOut;
+                t2[((size_t)i * lpw + e) * 2 + 0] = ina ? lg2(sa, kWeightBias) : kOut;
+                t2[((size_t)i * lpw + e) * 2 + 1] = inb ? lg2(sb, kWeightBias) : kOut;
+            }
+        CK(cudaMalloc(&h->ltab_ups1_dev, t1.size() * sizeof(float)));
+        CK(cudaMalloc(&h->ltab_ups2_dev, t2.size() * sizeof(float)));
+        CK(cudaMemcpy(h->ltab_ups1_dev, t1.data(), t1.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->ltab_ups2_dev, t2.data(), t2.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&h->slut_dev, lut.size() * sizeof(float)));
     CK(cudaMemcpyAsync(h->slut_dev, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -408,6 +434,9 @@ extern "C" void jbf_destroy(jbf_handle* h) {
     cudaFree(h->stats_dev);
     cudaFree(h->q_count_dev);
     cudaFree(h->q_items_dev);
+    cudaFree(h->ups_tab_dev);
+    cudaFree(h->ltab_ups1_dev);
+    cudaFree(h->ltab_ups2_dev);
     cudaFree(h->alt.guide4);
     cudaFree(h->alt.q_count_dev);
     cudaFree(h->alt.q_items_dev);
@@ -593,7 +622,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
     p.flag_scale = h->flag_scale; p.kc = h->kc; p.kd = h->kd; p.slut = h->slut_dev; p.stats = h->stats_dev;
     p.q_count = h->q_count_dev + h->q_cur; p.q_count_prev = h->q_count_dev + (h->q_cur ^ 1);
     p.q_items = h->q_items_dev; p.q_capacity = (unsigned)h->q_capacity;
-    p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl;
+    p.mode = mode; p.depth_lo = depth_lo; p.wl = wl; p.hl = hl; p.ups_inv_x = nullptr; p.ups_inv_y = nullptr;
     p.xyz = h->xyz_out; p.fx = h->xyz_fx; p.fy = h->xyz_fy; p.cx = h->xyz_cx; p.cy = h->xyz_cy; p.y_img0 = h->xyz_yimg0;
     if (p.xyz && !h->fast) return fail(KDME_ENOTSUP, "the fused back-projection needs the fast kernel (default sigmas, r = 1..15)");
     if (h->fast) {
@@ -641,16 +670,53 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
             g.radius = h->radius;
             g.ncol_max = (int)(((long long)(TW + 2 * h->radius) * wl + h->width - 1) / h->width) + 2;
             g.nrow_max = (int)(((long long)(TH + 2 * h->radius) * hl + rows - 1) / rows) + 2;
-            g.ltab1 = h->ltab_generic1_dev;
-            g.ltab2 = h->ltab_generic_dev;
+            g.ltab1 = h->ltab_ups1_dev;
+            g.ltab2 = h->ltab_ups2_dev;
             const int ws_ = 2 * h->radius + 1;
             const size_t smem = (size_t)g.ncol_max * g.nrow_max * 8 + (size_t)(g.ncol_max + g.nrow_max + 1) * 4 +
-                                (size_t)ws_ * (ws_ + 1) * 16 + 16;
+                                (size_t)ws_ * (ws_ + kUpsPad) * 16 + 16;
             if (smem <= 200 * 1024) {
+                const int ntx = (p.width + TW - 1) / TW, nty = (rows + TH - 1) / TH;
+                if (!h->ups_tab_dev || h->ups_wl != wl || h->ups_hl != hl || h->ups_rows != rows) {
+                    // the lattice of (wl, hl) in this frame size, once: no 64-bit division is left in the kernel
+                    std::vector<int> tab((size_t)wl + hl + 2 * (size_t)(ntx + nty) + (size_t)p.width + rows, -1);
+                    for (int x = 0; x < wl; ++x) tab[x] = (int)(((2LL * x + 1) * p.width) / (2LL * wl));
+                    for (int y = 0; y < hl; ++y) tab[(size_t)wl + y] = (int)(((2LL * y + 1) * rows) / (2LL * hl));
+                    int* tx = tab.data() + wl + hl;
+                    int* ty = tx + 2 * ntx;
+                    for (int b = 0; b < ntx; ++b) {
+                        tx[2 * b] = upsample_first_site_at_or_after(b * TW - h->radius, p.width, wl);
+                        tx[2 * b + 1] = upsample_first_site_at_or_after(b * TW + TW + h->radius, p.width, wl);
+                    }
+                    for (int b = 0; b < nty; ++b) {
+                        ty[2 * b] = upsample_first_site_at_or_after(b * TH - h->radius, rows, hl);
+                        ty[2 * b + 1] = upsample_first_site_at_or_after(b * TH + TH + h->radius, rows, hl);
+                    }
+                    int* ix = ty + 2 * nty;      // inverse maps (fp64 refinement of upsampled pixels): column -> xl or -1
+                    int* iy = ix + p.width;
+                    for (int x = 0; x < wl; ++x) ix[tab[x]] = x;
+                    for (int y = 0; y < hl; ++y) iy[tab[(size_t)wl + y]] = y;
+                    CK(cudaStreamSynchronize(h->stream));
+                    cudaFree(h->ups_tab_dev);
+                    h->ups_tab_dev = nullptr;
+                    CK(cudaMalloc(&h->ups_tab_dev, tab.size() * sizeof(int)));
+                    CK(cudaMemcpy(h->ups_tab_dev, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+                    h->ups_wl = wl; h->ups_hl = hl; h->ups_rows = rows;
+                }
+                g.site_x = h->ups_tab_dev; g.site_y = h->ups_tab_dev + wl;
+                g.tile_xl = h->ups_tab_dev + wl + hl; g.tile_yl = g.tile_xl + 2 * ntx;
+                p.ups_inv_x = g.tile_yl + 2 * nty; p.ups_inv_y = p.ups_inv_x + p.width;
+                // site columns any thread can see: lattice points in 2r + 4 consecutive pixels
+                const int maxc = (int)(((long long)(2 * h->radius + 4) * wl + h->width - 1) / h->width);
+                auto kern = maxc <= 5 ? jbf_upsample_gather_kernel<TW, TH, 5>
+                          : maxc <= 8 ? jbf_upsample_gather_kernel<TW, TH, 8> : jbf_upsample_gather_kernel<TW, TH, 0>;
+                if (getenv("KDME_GATHER_GENERIC")) kern = jbf_upsample_gather_kernel<TW, TH, 0>;
                 static std::atomic<unsigned long long> attr_done{0};
                 const unsigned long long bit = 1ull << (h->device & 63);
                 if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-                    CK(cudaFuncSetAttribute(jbf_upsample_gather_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CK(cudaFuncSetAttribute(jbf_upsample_gather_kernel<TW, TH, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CK(cudaFuncSetAttribute(jbf_upsample_gather_kernel<TW, TH, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CK(cudaFuncSetAttribute(jbf_upsample_gather_kernel<TW, TH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     attr_done.fetch_or(bit, std::memory_order_release);
                 }
                 cudaLaunchConfig_t cfg = {};
@@ -663,7 +729,7 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = (pdl && !h->no_pdl) ? 1 : 0;
-                CK(cudaLaunchKernelEx(&cfg, jbf_upsample_gather_kernel<TW, TH>, p, g));
+                CK(cudaLaunchKernelEx(&cfg, kern, p, g));
                 h->last_variant = 0x1000 | 0x400;
                 rc = KDME_OK;
             }
@@ -692,9 +758,16 @@ static int launch_filter(jbf_handle* h, const float* depth, const uint32_t* guid
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = h->no_pdl ? 0 : 1;
-            if (h->radius <= 7) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<8>, p, h->radius));
-            else if (h->radius <= 10) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<16>, p, h->radius));
-            else CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<31>, p, h->radius));
+            const bool plain = p.mode != kStageUpsample && !p.depth_up && !p.depth_dn;
+#define KDME_REFINE(K)                                                                        \
+    do {                                                                                      \
+        if (plain) CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<K, true>, p, h->radius));     \
+        else CK(cudaLaunchKernelEx(&cfg, jbf_refine_kernel<K, false>, p, h->radius));          \
+    } while (0)
+            if (h->radius <= 7) KDME_REFINE(8);
+            else if (h->radius <= 10) KDME_REFINE(16);
+            else KDME_REFINE(31);
+#undef KDME_REFINE
         }
         return KDME_OK;
     }

@@ -102,6 +102,32 @@ __global__ void __launch_bounds__(TW * TH) presmooth_kernel(const PresmoothParam
     p.guide4[(long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx] = o;
 }
 
+// One output pixel: {rint(s0 / ws), rint(s1 / ws), rint(s2 / ws)} clamped to bytes and packed, bit-identical to
+// fminf(fmaxf(rintf(__fdiv_rn(s, ws)), 0), 255) per channel for 0 <= s <= 255 ws, ws >= 1 (the centre tap has weight
+// 1), without the three IEEE divisions: q = s * rcp(ws) lies within 6e-5 of the correctly rounded quotient (two
+// roundings of 2^-23 relative at magnitude <= 255), so the two can only round to different integers when q is that
+// close to a half-integer -- then, and only then, the exact divisions are evaluated (cold, out of line).  The
+// rounding itself is the 1.5 * 2^23 trick (round-to-nearest-even; the byte appears in the low mantissa bits).
+__device__ __noinline__ uint32_t presmooth_pack_exact(float s0, float s1, float s2, float ws) {
+    const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0, ws)), 0.f), 255.f);
+    const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1, ws)), 0.f), 255.f);
+    const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2, ws)), 0.f), 255.f);
+    return (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
+}
+__device__ __forceinline__ uint32_t presmooth_pack(float s0, float s1, float s2, float ws) {
+    const float kMagic = 12582912.0f, kTie = 2.5e-4f;
+    const float inv = rcp_approx(ws);
+    const float q0 = __fmul_rn(s0, inv), q1 = __fmul_rn(s1, inv), q2 = __fmul_rn(s2, inv);
+    const float m0 = __fadd_rn(q0, kMagic), m1 = __fadd_rn(q1, kMagic), m2 = __fadd_rn(q2, kMagic);
+    const float d0 = fabsf(__fsub_rn(q0, __fsub_rn(m0, kMagic))), d1 = fabsf(__fsub_rn(q1, __fsub_rn(m1, kMagic))),
+                d2 = fabsf(__fsub_rn(q2, __fsub_rn(m2, kMagic)));
+    // d in [0, 0.5]: the largest of the three decides
+    if (fmaxf(fmaxf(d0, d1), d2) > 0.5f - kTie) return presmooth_pack_exact(s0, s1, s2, ws);
+    const uint32_t b0 = min(__float_as_uint(m0) & 0x1ffu, 255u), b1 = min(__float_as_uint(m1) & 0x1ffu, 255u),
+                   b2 = min(__float_as_uint(m2) & 0x1ffu, 255u);
+    return b0 | (b1 << 8) | (b2 << 16);
+}
+
 // ksize == 5 (the reference's call): 13 taps fully unrolled, 4 pixels per thread along x.  Each
 // staged pixel is converted ONCE to float b, g, r and a packed u8x4 word, kept as four shared-memory
 // planes so a thread fetches its 8-column row segment with conflict-free 16-byte LDS; a tap is then
@@ -124,6 +150,42 @@ __global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const 
     constexpr int SW = TW + 2 * R;   // staged (used) columns per row
     // reflect-101 only matters for tiles that touch the image border (CTA-uniform)
     const bool interior = (x0 >= R) && (y0 >= R) && (x0 + TW + R <= p.width) && (y0 + TH + R <= p.height);
+    // Tiles whose 72 staged columns [x0 - 4, x0 + TW + 4) lie inside the row, on 4-byte aligned rows (CTA-uniform):
+    // a thread stages 4 pixels = 12 bytes = three 32-bit loads, splits them with shifts and stores each plane with one
+    // 16-byte STS -- 3 loads and 4 stores per 4 pixels instead of 12 and 16.  Rows reflect (101) as in the general path.
+    const bool wide = (x0 >= 4) && (x0 + TW + 4 <= p.width) &&
+                      (((reinterpret_cast<uintptr_t>(p.bgr) | reinterpret_cast<uintptr_t>(p.bgr_up) |
+                         reinterpret_cast<uintptr_t>(p.bgr_dn) | (uintptr_t)p.bgr_step | (uintptr_t)p.bgr_frame_stride) & 3) == 0);
+    if (wide) {
+        constexpr int NG = SP / 4, GIT = (NG * SH + NT - 1) / NT;
+        uint32_t w0[GIT], w1[GIT], w2[GIT];
+#pragma unroll
+        for (int it = 0; it < GIT; ++it) {
+            const int g = tid + it * NT;
+            w0[it] = w1[it] = w2[it] = 0u;
+            if (g < NG * SH) {
+                const int sy = g / NG, gc = g - sy * NG;
+                int gy = y0 - R + sy;
+                if (!interior) gy = reflect101(gy, p.height);
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(presmooth_row(p, src, gy) + 3 * (x0 - 4 + 4 * gc));
+                w0[it] = __ldg(q); w1[it] = __ldg(q + 1); w2[it] = __ldg(q + 2);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < GIT; ++it) {
+            const int g = tid + it * NT;
+            if (g < NG * SH) {
+                const int sy = g / NG, gc = g - sy * NG;
+                const int o = sy * SP + 4 * gc;
+                // little endian: w0 = b0 g0 r0 b1 | w1 = g1 r1 b2 g2 | w2 = r2 b3 g3 r3
+                const uint32_t a = w0[it], b = w1[it], c = w2[it];
+                *reinterpret_cast<float4*>(sB + o) = make_float4((float)(a & 0xffu), (float)(a >> 24), (float)((b >> 16) & 0xffu), (float)((c >> 8) & 0xffu));
+                *reinterpret_cast<float4*>(sG + o) = make_float4((float)((a >> 8) & 0xffu), (float)(b & 0xffu), (float)(b >> 24), (float)((c >> 16) & 0xffu));
+                *reinterpret_cast<float4*>(sR + o) = make_float4((float)((a >> 16) & 0xffu), (float)((b >> 8) & 0xffu), (float)(c & 0xffu), (float)(c >> 24));
+                *reinterpret_cast<uint4*>(sP + o) = make_uint4(a & 0xffffffu, (a >> 24) | ((b & 0xffffu) << 8), (b >> 16) | ((c & 0xffu) << 16), c >> 8);
+            }
+        }
+    } else
     {   // warp w stages rows w, w + NWARP, ...; lane l columns l, l + 32, l + 64: no index division, the row pointer is
         // warp-uniform, and all byte loads of the thread are issued before the first use (memory-level parallelism)
         constexpr int NWARP = NT / 32, RIT = (SH + NWARP - 1) / NWARP, CIT = (SW + 31) / 32;
@@ -170,6 +232,7 @@ __global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const 
     // wavefronts bound the kernel); PY = 1 (one frame): twice the warps, half the serial work per thread.
     // Per pixel the taps are visited dy-major, dx-minor either way: same sums, same bits.
     const int lx = tid % (TW / 4), ly = tid / (TW / 4);   // ly indexes groups of PY rows
+    const uint32_t sCol_addr = smem_u32(sCol);
     uint32_t c[PY][4];
     float s0[PY][4], s1[PY][4], s2[PY][4], ws[PY][4];
 #pragma unroll
@@ -207,9 +270,10 @@ __global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int col = XO + k + dx;
+                    // IDP.4A with weights 4 and the table's shared-memory address as accumulator: the byte address of
+                    // sCol[L1 distance] in one instruction (no separate index scaling)
                     const uint32_t ad = __vabsdiffu4(rp[col], c[o][k]);
-                    const uint32_t l1 = __dp4a(ad, 0x01010101u, 0u);
-                    const float w = __fmul_rn(sw, sCol[l1]);
+                    const float w = __fmul_rn(sw, lds_f32(__dp4a(ad, 0x04040404u, sCol_addr)));
                     s0[o][k] = __fmaf_rn(w, rb[col], s0[o][k]);
                     s1[o][k] = __fmaf_rn(w, rg[col], s1[o][k]);
                     s2[o][k] = __fmaf_rn(w, rr[col], s2[o][k]);
@@ -227,10 +291,7 @@ __global__ void __launch_bounds__((TW / 4) * (TH / PY)) presmooth5_kernel(const 
         uint32_t ov[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float v0 = fminf(fmaxf(rintf(__fdiv_rn(s0[o][k], ws[o][k])), 0.f), 255.f);
-            const float v1 = fminf(fmaxf(rintf(__fdiv_rn(s1[o][k], ws[o][k])), 0.f), 255.f);
-            const float v2 = fminf(fmaxf(rintf(__fdiv_rn(s2[o][k], ws[o][k])), 0.f), 255.f);
-            ov[k] = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16);
+            ov[k] = presmooth_pack(s0[o][k], s1[o][k], s2[o][k], ws[o][k]);
         }
         uint32_t* dst = p.guide4 + (long long)frame * p.guide_frame_stride + (long long)gy * p.guide_pitch + gx;
         if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
