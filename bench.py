@@ -418,6 +418,16 @@ def main():
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / n_k
+    # the other launch of a step, alone: the guide pre-smooth of one chunk (inputs cycle through the shard: > L2)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_p = 0
+    p0.record()
+    for f0 in range(0, n_frames - args.chunk + 1, args.chunk):
+        jbf.presmooth(bgr[f0:f0 + args.chunk], out=guide4)
+        n_p += 1
+    p1.record()
+    torch.cuda.synchronize()
+    pre_ms = p0.elapsed_time(p1) / n_p
     clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -489,6 +499,8 @@ def main():
                          "peak_source": "MUFU.EX2 issue rate measured this run (tools/pipe_microbench)" if micro else "nominal 16/clk/SM"},
                 "pixels_per_launch": px_per_launch,
                 "kernel_ms_per_launch": kern_ms, "kernel_mpixel_s": px_per_launch / (kern_ms * 1e-3) / 1e6,
+                "presmooth_ms_per_launch": pre_ms,
+                "step_ms_per_chunk": ms_max / args.steps / n_chunks,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                         "peak_source": peaks_kind + " (MEASURED_PEAKS.json)", "bytes_per_pixel": BYTES_PER_PIXEL},
                 "traffic": traffic, "traffic_source": ("static: " + traffic_src + " (one ncu --set full capture of this kernel, "

@@ -172,12 +172,20 @@ class JointBilateralFilter:
         _lib.check(_lib.lib().jbf_process_batch(self._h, _ptr(depth), _ptr(color), 3 * self.width, _ptr(out), n))
         return out
 
-    def presmooth(self, color: torch.Tensor) -> torch.Tensor:
+    def presmooth(self, color: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """Guide pre-smooth only: [N,H,W,3] u8 -> internal guide [N,H,pitch] int32 words {B,G,R,0}."""
         _check_cuda(color, torch.uint8, "color", self.device)
+        if color.dim() != 4 or tuple(color.shape[1:]) != (self.height, self.width, 3):
+            raise ValueError(f"color must be [N, {self.height}, {self.width}, 3]")
         n = color.shape[0]
         pitch = (self.width + 3) & ~3
-        g4 = torch.empty((n, self.height, pitch), dtype=torch.int32, device=self.device)
+        if out is None:
+            g4 = torch.empty((n, self.height, pitch), dtype=torch.int32, device=self.device)
+        else:
+            _check_cuda(out, torch.int32, "out", self.device)
+            if tuple(out.shape) != (n, self.height, pitch):
+                raise ValueError(f"out must be [{n}, {self.height}, {pitch}]")
+            g4 = out
         _lib.check(_lib.lib().jbf_presmooth(self._h, _ptr(color), 3 * self.width, _ptr(g4), pitch * 4, n))
         return g4
 
