@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip parity / single-frame / configs[2..4] / strong-scaling blocks")
+    ap.add_argument("--no-extra", action="store_true", help="skip parity / single-frame / configs[2..4] / strong-scaling / guided fill / Buffer2D blocks")
     ap.add_argument("--band-size", type=int, default=16384, help="configs[4] frame edge")
     ap.add_argument("--config1", action="store_true",
                     help="configs[0] instead of the headline line: the bundled 640x480 frame, reference defaults "
@@ -463,6 +463,8 @@ def main():
             extra["single_frame"] = workloads.single()
             extra["upsample"] = workloads.upsample()
             extra["sweep"] = workloads.sweep(hbm_gbs=peaks0["hbm_gbs"])
+            extra["guided_fill"] = workloads.guided()
+            extra["buffer2d"] = workloads.buffer2d(hbm_gbs=peaks0["hbm_gbs"])
     else:
         parity = None
 

@@ -108,6 +108,30 @@ __global__ void __launch_bounds__(256) buf2d_kernel(float* __restrict__ buf, con
     }
 }
 
+// N-frame update of a SMALL buffer (one Kinect frame is 307 200 pixels): the update is a branchy serial recurrence
+// per pixel (a division per accepted frame), so with 4 pixels per thread a 640x480 buffer is 76 800 threads whose four
+// chains run one after the other -- a quarter of the GPU's thread slots, latency-bound (32 % of HBM).  One pixel per
+// thread gives the scheduler four times the warps to hide the chain's latency behind; loads stay coalesced (a warp
+// reads 128 contiguous bytes of each frame) and 8 frames are in flight per thread.  Same arithmetic, same order.
+__global__ void __launch_bounds__(256) buf2d_update_batch_px1_kernel(float* __restrict__ buf, const float* __restrict__ data,
+                                                                     long long n, int n_frames) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        float2 a = reinterpret_cast<float2*>(buf)[k];
+        constexpr int PF = 8;
+        for (int f0 = 0; f0 < n_frames; f0 += PF) {
+            float d[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (f0 + u < n_frames) d[u] = __ldg(data + (long long)(f0 + u) * n + k);
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (f0 + u < n_frames) update_weighted(a.x, a.y, d[u]);
+        }
+        reinterpret_cast<float2*>(buf)[k] = a;
+    }
+}
+
 // sensor millimetres (uint16, xn::DepthMetaData) -> float: 8 samples per thread (16-byte load, 2 x 16-byte store)
 __global__ void __launch_bounds__(256) u16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;

@@ -1363,6 +1363,16 @@ extern "C" int buf2d_update_batch_f32(buf2d_handle* b, const float* data_dev, in
     if (reinterpret_cast<uintptr_t>(data_dev) & 15) return fail(KDME_EINVAL, "buf2d_update: data must be 16-byte aligned");
     if (n_frames > 1 && (((long long)b->width * b->height) & 3))
         return fail(KDME_EINVAL, "buf2d_update_batch: width*height must be a multiple of 4 for batches");
+    const long long n = (long long)b->width * b->height;
+    if (n_frames > 1 && n < 148LL * 2048 * 4 && !getenv("KDME_BUF_BATCH_PX4")) {
+        // small buffer: one pixel per thread (four times the warps; see buf2d_update_batch_px1_kernel)
+        DeviceGuard g(b->device);
+        long long blocks = (n + 255) / 256;
+        if (blocks > 148LL * 8) blocks = 148LL * 8;
+        buf2d_update_batch_px1_kernel<<<(int)blocks, 256, 0, b->stream>>>(b->dw, data_dev, n, n_frames);
+        CK(cudaGetLastError());
+        return KDME_OK;
+    }
     return buf_launch<kBufUpdate>(b, data_dev, nullptr, n_frames);
 }
 extern "C" int buf2d_update_f32(buf2d_handle* b, const float* data_dev) { return buf2d_update_batch_f32(b, data_dev, 1); }

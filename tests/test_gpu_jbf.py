@@ -249,6 +249,36 @@ def test_presmooth_bit_exact_vs_oracle(golden_dir):
         assert np.array_equal(got, oracle.presmooth(im))
 
 
+def _presmooth_bytes(f, img):
+    g = f.presmooth(torch.from_numpy(np.ascontiguousarray(img)[None]).cuda())[0].cpu().numpy().view(np.uint32)
+    g = g[:, :img.shape[1]]                      # the pitch is rounded up to 4 words: the pad columns are not written
+    assert (g >> 24).max() == 0
+    return np.stack([(g >> s) & 0xFF for s in (0, 8, 16)], axis=-1).astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h", [(640, 96), (203, 61), (136, 40), (72, 33), (68, 20)])
+def test_presmooth_rounding_ties_and_staging_paths(w, h):
+    """The pre-smooth output byte is rint(sum / weight).  The kernel rounds s * rcp(ws) and falls back to the IEEE
+    division only next to a half-integer, so images built to produce exact ties (two-valued patterns whose
+    weighted means are k + 0.5) and near-ties must still match the oracle bit for bit; widths cover the 12-byte
+    vector staging (tiles whose 72 columns lie inside 4-byte aligned rows), the byte-wise staging (row pitch
+    3*203 is not a multiple of 4) and tiles that reflect at the border."""
+    rng = np.random.default_rng(w * 1000 + h)
+    f = _jbf_cls()(w, h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    images = []
+    for (a, b, sx, sy) in [(10, 11, 1, 1), (100, 103, 2, 1), (0, 255, 1, 2), (200, 201, 3, 3), (7, 8, 2, 2)]:
+        pat = (((xx // sx) + (yy // sy)) & 1).astype(np.uint8)
+        images.append(np.repeat((a + (b - a) * pat)[..., None], 3, axis=-1).astype(np.uint8))
+    stripes = np.where((xx % 4) < 2, 50, 51).astype(np.uint8)
+    images.append(np.stack([stripes, 255 - stripes, stripes // 2], axis=-1))
+    images.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    images.append((rng.integers(0, 4, (h, w, 3)) + 120).astype(np.uint8))        # low contrast: every weight near 1
+    images.append(np.full((h, w, 3), 255, np.uint8))
+    for im in images:
+        assert np.array_equal(_presmooth_bytes(f, im), oracle.presmooth(im))
+
+
 def test_process_on_bundled_frame_reference_defaults(golden_dir):
     """Config 1: bundled input/color.jpg with the reference's defaults (window 5, 70/50/20, pre-smooth
     5/30/30).  input/depth.xml is a stripped blob in the reference checkout; a seeded surrogate depth

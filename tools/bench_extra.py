@@ -53,32 +53,7 @@ def sweep():
 
 
 def buffer2d():
-    res = []
-    for (w, h, nf) in [(640, 480, 1), (3840, 2160, 1), (640, 480, 256)]:
-        b = Buffer2D(w, h)
-        frames = torch.rand((max(nf, 16), h, w), device="cuda") * 3000 + 500
-        outp = torch.empty((h, w), device="cuda")
-        px = w * h
-        it = iter(range(10 ** 9))
-
-        def upd():
-            b.updateData(frames[next(it) % frames.shape[0]])
-        ms_u = ev_time(upd, 50)
-        ms_i = ev_time(lambda: b.insertData(frames[0]), 50)
-        ms_g = ev_time(lambda: b.getDepthMap(outp), 50)
-        row = {"size": f"{w}x{h}", "update_us": ms_u * 1e3, "insert_us": ms_i * 1e3, "get_depth_us": ms_g * 1e3,
-               "update_gbs": px * 20 / ms_u / 1e6, "insert_gbs": px * 12 / ms_i / 1e6, "get_gbs": px * 12 / ms_g / 1e6}
-        if nf > 1:
-            ms_b = ev_time(lambda: b.updateData(frames[:nf]), 10)
-            # fused N-frame update: buffer read+written once (16 B/px) + N input planes (4 B/px each)
-            row.update({"fused_frames": nf, "fused_update_us": ms_b * 1e3,
-                        "fused_gbs": px * (16 + 4 * nf) / ms_b / 1e6,
-                        "fused_vs_per_frame_speedup": ms_u * nf / ms_b})
-        row["hbm_frac_update"] = row["update_gbs"] / PEAKS["hbm_gbs"]
-        res.append(row)
-        b.close()
-    print(json.dumps({"workload": "Buffer2D (ArrayBuffer/Buffer2D.cu) kernels; algorithmic bytes 20/12/12 B per pixel",
-                      "hbm_peak_gbs": PEAKS["hbm_gbs"], "rows": res}))
+    print(json.dumps(workloads.buffer2d(hbm_gbs=PEAKS["hbm_gbs"])))
 
 
 def upsample():
@@ -86,16 +61,7 @@ def upsample():
 
 
 def guided():
-    from kinectdepthmapenhancement_b200 import guided_fill
-    w, h = 1920, 1080
-    d, c = synth.rgbd_frame(w, h, seed=6, frame=1, device="cuda")
-    lab = ((torch.arange(h, device="cuda")[:, None] // 40) * 64 + (torch.arange(w, device="cuda")[None, :] // 40)).int().contiguous()
-    out = torch.empty_like(d)
-    ms_l = ev_time(lambda: guided_fill(d, c, lab, 3, out=out), 20)
-    ms_n = ev_time(lambda: guided_fill(d, c, None, 3, out=out), 20)
-    print(json.dumps({"workload": "guided cross-bilateral fill (depthmap_enhancement) 1920x1080, window 7, sigmas 30/50/70",
-                      "ms_with_labels": ms_l, "ms_no_labels": ms_n, "mpixel_s_with_labels": w * h / ms_l / 1e3,
-                      "algorithmic_bytes": w * h * (4 + 3 + 4 + 4), "hbm_gbs_algorithmic": w * h * 15 / ms_l / 1e6}))
+    print(json.dumps(workloads.guided()))
 
 
 def single():
