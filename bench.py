@@ -465,6 +465,7 @@ def main():
             extra["sweep"] = workloads.sweep(hbm_gbs=peaks0["hbm_gbs"])
             extra["guided_fill"] = workloads.guided()
             extra["buffer2d"] = workloads.buffer2d(hbm_gbs=peaks0["hbm_gbs"])
+            extra["next_rows"] = workloads.next_rows()
     else:
         parity = None
 

@@ -6,6 +6,7 @@
   python tools/bench_extra.py upsample   # configs[2]: 512x424 ToF depth -> 1920x1080 guide
   python tools/bench_extra.py single     # one 640x480 frame per call (latency of Process)
   python tools/bench_extra.py guided     # guided cross-bilateral fill at 1920x1080
+  python tools/bench_extra.py next_rows  # f1-f4 (MRF, cloud bilateral, projectiveToReal, mean 3-D error) per call
   torchrun ... tools/bench_extra.py band # configs[4]: 16384x16384 r=9 row bands + NVLink halo exchange
 
 Each prints one JSON object; copies are kept under profiles/.
@@ -68,6 +69,10 @@ def single():
     print(json.dumps(workloads.single()))
 
 
+def next_rows():
+    print(json.dumps(workloads.next_rows()))
+
+
 def band():
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -84,4 +89,4 @@ def band():
 
 
 if __name__ == "__main__":
-    {"sweep": sweep, "buffer2d": buffer2d, "upsample": upsample, "single": single, "band": band, "guided": guided}[sys.argv[1]]()
+    {"sweep": sweep, "buffer2d": buffer2d, "upsample": upsample, "single": single, "band": band, "guided": guided, "next_rows": next_rows}[sys.argv[1]]()

@@ -130,6 +130,33 @@ def buffer2d(hbm_gbs: float = 6551.0):
             "hbm_peak_gbs": hbm_gbs, "rows": res}
 
 
+# ------------------------------------------------------------------ the "next" rows f1-f4 at Kinect size
+def next_rows(iters: int = 50):
+    """MarkovRandomField (f1), Projection_GPU::bilateralfilter on clouds (f2), projectiveToReal alone and fused into the
+    filter epilogue (f3), the mean 3-D error reduction (f4) on one 640x480 frame: microseconds per call."""
+    from kinectdepthmapenhancement_b200 import evalio
+    from kinectdepthmapenhancement_b200.jbf import projective_to_real
+    w, h = 640, 480
+    d, c = synth.rgbd_frame(w, h, seed=1, frame=0, device="cuda")
+    f = JointBilateralFilter(w, h, window_radius=2)
+    pts = projective_to_real(d, 525.0, 525.0, w // 2, h // 2)
+    z = torch.where(pts[..., 2] > 0, pts[..., 2], torch.ones_like(pts[..., 2]))
+    norm = pts.clone()
+    norm[..., 0] /= z
+    norm[..., 1] /= z
+    norm = norm.contiguous()
+    xyz = torch.empty((h, w, 3), device="cuda")
+    res = {"workload": "next rows on one 640x480 frame (window 5): microseconds per call, launch latency included",
+           "f1_mrf_us": ev_time(lambda: f.mrf(d, c), iters) * 1e3,
+           "f2_depth_bilateral_xyz_us": ev_time(lambda: evalio.depth_bilateral_xyz(norm, pts), iters) * 1e3,
+           "f3_projective_to_real_us": ev_time(lambda: projective_to_real(d, 525.0, 525.0, w // 2, h // 2), iters) * 1e3,
+           "f3_process_then_project_us": ev_time(lambda: (f.Process(d, c), projective_to_real(f.getFiltered_Device(), 525.0, 525.0, w // 2, h // 2)), iters) * 1e3,
+           "f3_process_xyz_fused_us": ev_time(lambda: f.process_xyz(d, c, 525.0, 525.0, w // 2, h // 2, out=xyz), iters) * 1e3,
+           "f4_mean_3d_error_us": ev_time(lambda: evalio.mean_3d_error(xyz, pts), iters) * 1e3}
+    f.close()
+    return res
+
+
 # ------------------------------------------------------------------ configs[3]: radius sweep
 def sweep(radii=range(3, 16), hbm_gbs: float = 6551.0, iters: int = 5):
     w, h, nf = 3840, 2160, 8
