@@ -448,7 +448,12 @@ def main():
     extra = {}
     if not args.no_extra:
         extra["strong"] = workloads.strong(jbf, depth, bgr, out, min(4096, n_frames * world))
-        parity = parity_report(JointBilateralFilter, depth, bgr, (0, 17, 33, 63)) if rank == 0 else None
+        parity = None
+        if rank == 0:
+            try:
+                parity = parity_report(JointBilateralFilter, depth, bgr, (0, 17, 33, 63))
+            except Exception as e:   # noqa: BLE001 -- reported, never hidden
+                parity = {"error": f"{type(e).__name__}: {e}"}
         del depth, bgr, out, guide4
         jbf.close()
         torch.cuda.empty_cache()
@@ -460,12 +465,17 @@ def main():
             torch.cuda.empty_cache()
         if rank == 0:
             peaks0, _ = measured_peaks()
-            extra["single_frame"] = workloads.single()
-            extra["upsample"] = workloads.upsample()
-            extra["sweep"] = workloads.sweep(hbm_gbs=peaks0["hbm_gbs"])
-            extra["guided_fill"] = workloads.guided()
-            extra["buffer2d"] = workloads.buffer2d(hbm_gbs=peaks0["hbm_gbs"])
-            extra["next_rows"] = workloads.next_rows()
+            # secondary blocks never take the headline line down with them: a failure is reported in place
+            for key, fn in (("single_frame", workloads.single), ("upsample", workloads.upsample),
+                            ("sweep", lambda: workloads.sweep(hbm_gbs=peaks0["hbm_gbs"])),
+                            ("guided_fill", workloads.guided),
+                            ("buffer2d", lambda: workloads.buffer2d(hbm_gbs=peaks0["hbm_gbs"])),
+                            ("next_rows", workloads.next_rows)):
+                try:
+                    extra[key] = fn()
+                except Exception as e:   # noqa: BLE001 -- reported, never hidden
+                    extra[key] = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.empty_cache()
     else:
         parity = None
 
@@ -514,7 +524,10 @@ def main():
             "parity": parity, "extra": extra, "microbench": micro,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            except Exception as e:   # noqa: BLE001 -- reported, never hidden
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
