@@ -81,8 +81,12 @@ int jbf_refine_stats(jbf_handle *h, unsigned long long *refined, unsigned long l
 
 /* Same operator over n_frames independent frames stored back to back (frame
  * stride width*height elements / height*bgr_step bytes); out_dev receives
- * n_frames planes.  One launch pair for the whole batch (the B200-native form of
- * calling Process once per captured frame, main.cpp:86-101 loop shape). */
+ * n_frames planes.  One launch triple (pre-smooth, filter, fp64 refinement) per chunk
+ * of max_batch frames (the B200-native form of calling Process once per captured
+ * frame, main.cpp:86-101 loop shape).  With more than one chunk, the chunks alternate
+ * between the handle's stream and an internal one, forked and joined by events: the
+ * call is ordered after the stream's earlier work, and the stream's later work after
+ * all of it (plain stream semantics; results do not depend on the chunking). */
 int jbf_process_batch(jbf_handle *h, const float *depth_dev, const uint8_t *bgr_dev, size_t bgr_step,
                       float *out_dev, int n_frames);
 
