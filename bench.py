@@ -139,6 +139,26 @@ def measured_traffic(pixels_per_launch: int):
     return total * pixels_per_launch / prof_pixels, os.path.relpath(files[-1], ROOT)
 
 
+def profiled_pipes():
+    """Pipe utilisation of the dominant kernel from the same committed ncu capture (static, labelled as such):
+    what the hardware pipes were doing, beside the algorithmic-flop fraction."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_jbf_fast_r7_*.ncu.txt")))
+    if not files:
+        return None
+    txt = open(files[-1]).read()
+    out = {"source": "static: " + os.path.relpath(files[-1], ROOT)}
+    for key, name in (("xu_pipe_busy_pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                      ("fma_pipe_busy_pct", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                      ("alu_pipe_busy_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                      ("issue_slots_busy_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active")):
+        m = re.search(re.escape(name) + r"\s+([0-9.]+)", txt)
+        if m:
+            out[key] = float(m.group(1))
+    return out
+
+
 def cpu_baseline(budget_s: float, frames_np=None):
     """The reference's own kernel text on the host cores (oracle/_ref), else the C restatement (port)."""
     import numpy as np
@@ -516,6 +536,7 @@ def main():
                 "step_ms_per_chunk": ms_max / args.steps / n_chunks,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"],
                         "peak_source": peaks_kind + " (MEASURED_PEAKS.json)", "bytes_per_pixel": BYTES_PER_PIXEL},
+                "pipes_ncu": profiled_pipes(),
                 "traffic": traffic, "traffic_source": ("static: " + traffic_src + " (one ncu --set full capture of this kernel, "
                                                        "scaled by pixels; not measured in this run)") if traffic_src else None,
                 "algorithmic_bytes_per_launch": px_per_launch * BYTES_PER_PIXEL,
