@@ -75,6 +75,9 @@ struct JbfParams {
     // are cut into tiles of `ts` rows (a multiple of 2: whole warps), so that the work beyond a whole number
     // of big tiles per SM is spread over many SMs instead of landing on a few.  All big: nbig_rows = INT_MAX.
     int nbig_rows, ts;
+    // half_units != 0: every small tile appears twice in the grid (consecutive blockIdx.y), once per pixel pair --
+    // see jbf_fast_body's PSEL
+    int half_units;
     // peer-memory halos (row bands over NVLink): rows [band0, band1) of the arrays are this rank's own;
     // when depth_up / depth_dn are non-null, rows above / below are read straight from the neighbour
     // GPU's band through these peer-mapped pointers (depth_up + row*W for row < band0,
@@ -135,10 +138,14 @@ __device__ __forceinline__ void two_sum2(f32x2& a, const f32x2 b, f32x2& lo) {
     lo = add2(lo, t);
 }
 
-template <int R, int TW, int TH, int MINB>
-__global__ void __launch_bounds__((TW / 4) * TH, MINB)
-jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_constant__ CUtensorMap tm_guide,
-                const JbfParams p) {
+// PSEL: 0 = the thread computes its 4 pixels; 1 / 2 = only pixels (0,1) / (2,3) of its group -- a HALF work unit: the
+// other pair's instruction stream does not exist in that instantiation, so the warp costs half the MUFU / FMA time.
+// Launches of a few waves hand the tiles beyond a whole number per SM out as such halves (JbfParams::half_units):
+// a warp instruction costs the same pipe time however few lanes are active (tools/mufu_lanes.cu), so work can only
+// be cut finer than a warp by dropping instructions.  Same arithmetic per pixel (the accumulation origin is still
+// that of the 4-pixel group): results are bit-identical whichever way a pixel is computed.
+template <int R, int TW, int TH, int PSEL>
+__device__ __forceinline__ void jbf_fast_body(const CUtensorMap& tm_depth, const CUtensorMap& tm_guide, const JbfParams& p) {
     using T = JbfTile<R, TW, TH>;
     constexpr int WS = T::WS, RP = T::RP, SP = T::SP, SH = T::SH, NT = T::NT, NW = T::NW, C0 = T::C0;
     constexpr int LPP = T::LPP;
@@ -157,7 +164,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     const int th_eff = big ? TH : p.ts;                       // rows of this tile
     const int she = th_eff + 2 * R;                           // staged rows this tile needs
     const int x0 = blockIdx.x * TW, frame = blockIdx.z;
-    const int y0 = p.y_off + (big ? (int)blockIdx.y * TH : p.nbig_rows * TH + ((int)blockIdx.y - p.nbig_rows) * p.ts);
+    const int small_idx = ((int)blockIdx.y - p.nbig_rows) >> (p.half_units ? 1 : 0);   // two half units per small tile
+    const int y0 = p.y_off + (big ? (int)blockIdx.y * TH : p.nbig_rows * TH + small_idx * p.ts);
     const int sx0 = x0 - RP, sy0 = y0 - R;  // image coords of staged (0,0)
     // a tile whose halo crosses into a neighbour GPU's rows stages with plain loads (peer pointers);
     // every other tile keeps the launch's staging mode (CTA-uniform)
@@ -353,6 +361,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 const f32x2 dsh2 = pack2(dsh, dsh);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */
                     const int j0 = c - C0 - 2 * pr;   // tap column index of the pair's first pixel; second uses j0-1
                     const bool v0 = (j0 >= 0 && j0 < WS), v1 = (j0 - 1 >= 0 && j0 - 1 < WS);
                     if (v0 && v1) {
@@ -383,10 +392,12 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
             // row sums -> sums of a group of kRowsPer2Sum rows (plain adds: a fraction of the window's magnitude)
             // -> window sums (2Sum, error-free)
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) { gaccP[pr] = add2(gaccP[pr], raccP[pr]); gwsP[pr] = add2(gwsP[pr], rwsP[pr]); }
+            for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */ gaccP[pr] = add2(gaccP[pr], raccP[pr]); gwsP[pr] = add2(gwsP[pr], rwsP[pr]); }
             if ((i % kRowsPer2Sum) == kRowsPer2Sum - 1 || i == WS - 1) {
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */
                     two_sum2(accP[pr], gaccP[pr], accL[pr]);
                     two_sum2(wsP[pr], gwsP[pr], wsL[pr]);
                     gaccP[pr] = 0ull; gwsP[pr] = 0ull;
@@ -429,6 +440,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 const f32x2 ndsh2 = pack2(-dsh, -dsh);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */
                     const int j0 = c - C0 - 2 * pr;
                     const bool v0 = (j0 >= 0 && j0 < WS), v1 = (j0 - 1 >= 0 && j0 - 1 < WS);
                     if (v0 && v1) {
@@ -462,7 +474,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 }
             }
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) { numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
+            for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */ numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
         }
         unpack2(numP[0], num[0], num[1]); unpack2(numP[1], num[2], num[3]);
         unpack2(denP[0], den[0], den[1]); unpack2(denP[1], den[2], den[3]);
@@ -483,6 +496,7 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 const f32x2 dsh2 = pack2(dsh, dsh);
 #pragma unroll
                 for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */
                     const int j0 = c - C0 - 2 * pr;
                     const bool v0 = (j0 >= 0 && j0 < WS), v1 = (j0 - 1 >= 0 && j0 - 1 < WS);
                     if (v0 && v1) {
@@ -520,7 +534,8 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 }
             }
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr) { numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
+            for (int pr = 0; pr < 2; ++pr) {
+                    if (PSEL != 0 && pr != PSEL - 1) continue;   /* compile time */ numP[pr] = add2(numP[pr], rnumP[pr]); denP[pr] = add2(denP[pr], rdenP[pr]); }
         }
         unpack2(numP[0], num[0], num[1]); unpack2(numP[1], num[2], num[3]);
         unpack2(denP[0], den[0], den[1]); unpack2(denP[1], den[2], den[3]);
@@ -571,11 +586,12 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
     if (oy < p.out_rows && gx < p.width) {
         const long long pix = (long long)frame * p.width * p.out_rows + (long long)oy * p.width + gx;
         float* dst = p.out + pix;
-        if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        constexpr int K0 = (PSEL == 2) ? 2 : 0, K1 = (PSEL == 1) ? 2 : 4;   // the pixels this instantiation owns
+        if (PSEL == 0 && gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
             stg_stream_f4(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = K0; k < K1; ++k)
                 if (gx + k < p.width) dst[k] = o[k];
         }
         if (p.xyz != nullptr) {
@@ -591,17 +607,32 @@ jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_const
                 v3[3 * k + 2] = o[k];
             }
             float* xdst = p.xyz + 3 * pix;
-            if (gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(xdst) & 15) == 0)) {
+            if (PSEL == 0 && gx + 3 < p.width && ((reinterpret_cast<uintptr_t>(xdst) & 15) == 0)) {
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     stg_stream_f4(reinterpret_cast<float4*>(xdst) + q,
                                   make_float4(v3[4 * q], v3[4 * q + 1], v3[4 * q + 2], v3[4 * q + 3]));
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = K0; k < K1; ++k)
                     if (gx + k < p.width) { xdst[3 * k] = v3[3 * k]; xdst[3 * k + 1] = v3[3 * k + 1]; xdst[3 * k + 2] = v3[3 * k + 2]; }
             }
         }
+    }
+}
+
+template <int R, int TW, int TH, int MINB>
+__global__ void __launch_bounds__((TW / 4) * TH, MINB)
+jbf_fast_kernel(const __grid_constant__ CUtensorMap tm_depth, const __grid_constant__ CUtensorMap tm_guide,
+                const JbfParams p) {
+    // CTA-uniform dispatch: whole tiles and whole small tiles run the full body, half units one pair each.  The 64x16
+    // instantiations (large launches) carry the full body only: the hot kernel's code is exactly the single-body one.
+    if constexpr (TH >= 16) {
+        jbf_fast_body<R, TW, TH, 0>(tm_depth, tm_guide, p);
+    } else {
+        if (!p.half_units || (int)blockIdx.y < p.nbig_rows) jbf_fast_body<R, TW, TH, 0>(tm_depth, tm_guide, p);
+        else if ((((int)blockIdx.y - p.nbig_rows) & 1) == 0) jbf_fast_body<R, TW, TH, 1>(tm_depth, tm_guide, p);
+        else jbf_fast_body<R, TW, TH, 2>(tm_depth, tm_guide, p);
     }
 }
 

@@ -165,7 +165,7 @@ struct jbf_handle {
     // gather-form upsampling: the site lattice tabulated for (ups_wl, ups_hl, ups_rows): site_x[wl], site_y[hl],
     // tile_xl[tiles_x][2], tile_yl[tiles_y][2]
     int* ups_tab_dev = nullptr; int ups_wl = 0, ups_hl = 0, ups_rows = 0;
-    bool one_lane = false;
+    bool one_lane = false, no_half_units = false;
     // fused back-projection (jbf_process_xyz): set for one launch
     float* xyz_out = nullptr; float xyz_fx = 0, xyz_fy = 0; int xyz_cx = 0, xyz_cy = 0, xyz_yimg0 = 0;
     // host pipeline (jbf_process_host)
@@ -352,6 +352,7 @@ static int build_tables(jbf_handle* h) {
     h->no_split_tiles = getenv("KDME_NO_SPLIT_TILES") != nullptr;
     h->no_pdl = getenv("KDME_NO_PDL") != nullptr;
     h->one_lane = getenv("KDME_ONE_LANE") != nullptr;
+    h->no_half_units = getenv("KDME_NO_HALF_UNITS") != nullptr;
     if (const char* th = getenv("KDME_TILE_H")) h->force_tile_h = atoi(th);
     if (const char* rl = getenv("KDME_RES_LIMIT")) h->res_limit = atoi(rl);
     h->kc = h->use_color ? 1.0 / (2.0 * (double)h->sigma_c * (double)h->sigma_c) : 0.0;
@@ -554,9 +555,22 @@ static int launch_fast_rt(jbf_handle* h, JbfParams p, bool want_tma, int rows, b
     // tiles (one warp each), so the surplus spreads over many SMs instead of giving a few SMs one more big tile.
     const int tx = (p.width + TW - 1) / TW;
     int tile_rows = (p.out_rows + TH - 1) / TH;
-    p.nbig_rows = INT_MAX; p.ts = 2;
+    p.nbig_rows = INT_MAX; p.ts = 2; p.half_units = 0;
     const long long ctas = (long long)tx * tile_rows * p.n_frames;
-    if (!h->no_split_tiles && TH > 2 && ctas < 148LL * 12 && ctas % 148 != 0) {
+    const long long slots = 148LL * MINB;   // CTAs of this instantiation the GPU holds at once
+    if (!h->no_half_units && TH > 2 && TH < 16 && ctas <= slots && 2 * ctas > 148) {   // (64x16 kernels: full body only)
+        // Less than one wave of tiles (one Kinect frame: 600 tiles of 64x8 on 1184 slots): every SM sub-partition
+        // would hold ~4 warps, and at that occupancy a warp's run time is set by the length of its own instruction
+        // stream (latency-bound: 61 % issue slots against 72 % with the 8 warps of batch mode).  Every tile goes out
+        // as two HALF units instead (jbf_fast_body's PSEL: one pixel pair each; the tile is staged twice, the
+        // instruction streams are halves): twice the warps, each half as long -- 72.6 -> 67.9 us per Kinect frame at
+        // r = 7.  (Keeping a few tiles whole so that the launch fits one wave is worse, 100 us: a whole tile then
+        // takes twice as long as everything around it.)
+        p.nbig_rows = 0; p.ts = TH; p.half_units = 1;
+        tile_rows = 2 * tile_rows;
+    } else if (!h->no_split_tiles && TH > 2 && ctas < 148LL * 12 && ctas % 148 != 0) {
+        // A few waves: keep a whole number of TH-row tiles per SM and cut the image rows left over into 2-row tiles
+        // (one warp each), so the surplus spreads over many SMs instead of giving a few SMs one more big tile.
         const long long per_sm = ctas / 148;
         const int nbig = (int)std::min<long long>(tile_rows, (per_sm * 148) / ((long long)tx * p.n_frames));
         const int rem = p.out_rows - nbig * TH;
