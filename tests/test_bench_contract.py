@@ -39,6 +39,24 @@ def test_reference_arm_non_zero_rank_is_silent():
     assert res.returncode == 0 and res.stdout.strip() == ""
 
 
+def test_static_roofline_fields_parse_from_committed_profiles():
+    """roofline.traffic and roofline.pipes_ncu come from the committed `ncu --set full` summary of the dominant kernel
+    (labelled static in the line): the parser must find the newest capture and its counters."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, src = bench.measured_traffic(64 * 640 * 480)
+    assert src and src.startswith("profiles/") and "jbf_fast_r7" in src
+    # no wasted re-reads: DRAM traffic of a 64-frame launch within 10 % of the 11 B/pixel algorithmic bytes
+    assert 0.9 * 64 * 640 * 480 * 11 < traffic < 1.1 * 64 * 640 * 480 * 12
+    pipes = bench.profiled_pipes()
+    assert pipes["source"].endswith(src)
+    for k in ("xu_pipe_busy_pct", "fma_pipe_busy_pct", "alu_pipe_busy_pct", "issue_slots_busy_pct"):
+        assert 0.0 < pipes[k] <= 100.0
+    assert pipes["xu_pipe_busy_pct"] > pipes["fma_pipe_busy_pct"]      # the kernel is MUFU-bound, not FP32-bound
+
+
 @pytest.mark.gpu
 def test_gpu_arm_line():
     line = _run(["--frames", "256", "--steps", "2", "--warmup", "3", "--e2e-frames", "128", "--cpu-seconds", "3",
